@@ -1,0 +1,224 @@
+// FP64 DMMA GEMM, see gemm.cuh.  Column-major operands, C = alpha op(A) op(B) + beta C.
+//
+// Tiling: CTA tile BM x BN x BK, warp tile WM x WN built from m8n8k4 DMMA atoms.  Operand
+// tiles are staged global -> shared with 16-byte cp.async (LDGSTS, zero-fill predication at
+// element granularity) through a STAGES-deep ring; the shared layouts keep the global
+// contiguous direction and are padded to stride = 4 (mod 16) doubles so that the one-element-
+// per-lane DMMA fragment reads are bank-conflict free:
+//     !TA: sA[k][m]  ld = BM+4      TA: sA[m][k]  ld = BK+4
+//     !TB: sB[n][k]  ld = BK+4      TB: sB[k][n]  ld = BN+4
+#include "gemm.cuh"
+
+#include <atomic>
+
+namespace gscfb {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
+
+template <int BM, int BN, int BK, bool TA, bool TB>
+struct SmemLayout {
+  static constexpr int A_CE = TA ? BK : BM;  // contiguous extent
+  static constexpr int A_SE = TA ? BM : BK;  // strided extent
+  static constexpr int B_CE = TB ? BN : BK;
+  static constexpr int B_SE = TB ? BK : BN;
+  static constexpr int A_LD = A_CE + 4;
+  static constexpr int B_LD = B_CE + 4;
+  static constexpr int A_ELEMS = A_SE * A_LD;
+  static constexpr int B_ELEMS = B_SE * B_LD;
+  static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+};
+
+// Copy one operand tile into shared memory.  CE/SE/LD as in SmemLayout; (c0, s0) = tile origin
+// along the contiguous / strided global direction; (climit, slimit) = matrix extents.
+template <int CE, int SE, int LD, int NT, int VEC>
+__device__ __forceinline__ void load_operand(double* __restrict__ s, const double* __restrict__ g,
+                                             int ld, int c0, int s0, int climit, int slimit) {
+  constexpr int CPR = CE / VEC;  // chunks per strided index
+  constexpr int TOTAL = CPR * SE;
+#pragma unroll
+  for (int c = threadIdx.x; c < TOTAL; c += NT) {
+    const int si = c / CPR;
+    const int ci = (c - si * CPR) * VEC;
+    const int gc = c0 + ci, gs = s0 + si;
+    int valid = climit - gc;
+    valid = valid < 0 ? 0 : (valid > VEC ? VEC : valid);
+    if (gs >= slimit) valid = 0;
+    const double* src = valid > 0 ? g + (size_t)gs * ld + gc : g;
+    if (VEC == 2)
+      cp_async16(s + si * LD + ci, src, valid * 8);
+    else
+      cp_async8(s + si * LD + ci, src, valid * 8);
+  }
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+dgemm_dmma_kernel(const GemmParams p) {
+  using L = SmemLayout<BM, BN, BK, TA, TB>;
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  constexpr int MI = WM / 8, NI = WN / 8;
+  extern __shared__ __align__(16) double smem[];
+
+  // ---- resolve this CTA's problem ---------------------------------------------------------
+  const double* A;
+  const double* B;
+  double* C;
+  int m, n, k, lda, ldb, ldc;
+  double alpha, beta;
+  if (p.descs != nullptr) {
+    const GemmDesc d = p.descs[blockIdx.z];
+    A = d.A; B = d.B; C = d.C; m = d.m; n = d.n; k = d.k;
+    lda = d.lda; ldb = d.ldb; ldc = d.ldc; alpha = d.alpha; beta = d.beta;
+  } else {
+    const long long z = p.batch_map ? p.batch_map[blockIdx.z] : blockIdx.z;
+    A = p.A + z * p.sA; B = p.B + z * p.sB; C = p.C + z * p.sC;
+    m = p.m; n = p.n; k = p.k; lda = p.lda; ldb = p.ldb; ldc = p.ldc;
+    alpha = p.alpha; beta = p.beta;
+  }
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= m || n0 >= n) return;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  const bool alignedA = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((lda & 1) == 0) &&
+                        ((p.skA & 1) == 0);
+  const bool alignedB = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((ldb & 1) == 0) &&
+                        ((p.skB & 1) == 0);
+
+  const int kbatch = p.descs ? 1 : p.kbatch;
+  const int ktiles_per = (k + BK - 1) / BK;
+  const int KT = ktiles_per * kbatch;
+
+  auto load_tile = [&](int stage, int t) {
+    const int q = t / ktiles_per;
+    const int k0 = (t - q * ktiles_per) * BK;
+    double* sA = smem + stage * L::STAGE_ELEMS;
+    double* sB = sA + L::A_ELEMS;
+    const double* Aq = A + (size_t)q * p.skA;
+    const double* Bq = B + (size_t)q * p.skB;
+    if (TA) {  // A stored k x m: contiguous along k
+      if (alignedA) load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 2>(sA, Aq, lda, k0, m0, k, m);
+      else          load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 1>(sA, Aq, lda, k0, m0, k, m);
+    } else {   // A stored m x k: contiguous along m
+      if (alignedA) load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 2>(sA, Aq, lda, m0, k0, m, k);
+      else          load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 1>(sA, Aq, lda, m0, k0, m, k);
+    }
+    if (TB) {  // B stored n x k: contiguous along n
+      if (alignedB) load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 2>(sB, Bq, ldb, n0, k0, n, k);
+      else          load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 1>(sB, Bq, ldb, n0, k0, n, k);
+    } else {   // B stored k x n: contiguous along k
+      if (alignedB) load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 2>(sB, Bq, ldb, k0, n0, k, n);
+      else          load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 1>(sB, Bq, ldb, k0, n0, k, n);
+    }
+  };
+
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  for (int t = 0; t < KT; ++t) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int tn = t + STAGES - 1;
+      if (tn < KT) load_tile(tn % STAGES, tn);
+      cp_async_commit();
+    }
+    const double* sA = smem + (t % STAGES) * L::STAGE_ELEMS;
+    const double* sB = sA + L::A_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[MI], bf[NI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int r = wm + i * 8 + lr;
+        af[i] = TA ? sA[r * L::A_LD + kk + lc] : sA[(kk + lc) * L::A_LD + r];
+      }
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int c = wn + j * 8 + lr;
+        bf[j] = TB ? sB[(kk + lc) * L::B_LD + c] : sB[c * L::B_LD + kk + lc];
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue ----------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int r = m0 + wm + i * 8 + lr;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int c = n0 + wn + j * 8 + 2 * lc;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (c + h < n) {
+          double* dst = C + (size_t)(c + h) * ldc + r;
+          double v = alpha * acc[i][j][h];
+          if (beta != 0.0) v += beta * (*dst);
+          *dst = v;
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cudaStream_t st) {
+  using L = SmemLayout<BM, BN, BK, TA, TB>;
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
+  auto kern = dgemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
+  static bool configured = false;
+  if (!configured) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(ceil_div(max_m, BM), ceil_div(max_n, BN), batch);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return GSCF_B200_OK;
+  kern<<<grid, NT, smem, st>>>(p);
+  count_launch();
+  GSCF_CHECK_LAUNCH();
+  return GSCF_B200_OK;
+}
+
+template <bool TA, bool TB>
+static int launch_t(const GemmParams& p, int batch, int max_m, int max_n, cudaStream_t st) {
+  // Large tiles once the grid still covers the 148 SMs; small tiles otherwise.
+  const long long big_tiles = (long long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * batch;
+  if (big_tiles >= 120 && p.descs == nullptr)
+    return launch_cfg<128, 128, 16, 64, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
+  return launch_cfg<64, 64, 16, 32, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
+}
+
+int launch_gemm(bool ta, bool tb, const GemmParams& p, int batch, int max_m, int max_n,
+                cudaStream_t st) {
+  if (batch <= 0 || max_m <= 0 || max_n <= 0) return GSCF_B200_OK;
+  if (batch > 65535) {
+    set_last_error("gemm: batch > 65535 not supported in one launch");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
+  if (ta) return tb ? launch_t<true, true>(p, batch, max_m, max_n, st)
+                    : launch_t<true, false>(p, batch, max_m, max_n, st);
+  return tb ? launch_t<false, true>(p, batch, max_m, max_n, st)
+            : launch_t<false, false>(p, batch, max_m, max_n, st);
+}
+
+}  // namespace gscfb

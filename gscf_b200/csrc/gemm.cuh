@@ -1,0 +1,67 @@
+// FP64 tensor-core GEMM for sm_100a (DMMA.8x8x4 tiles fed through a cp.async pipeline).
+//
+// Replaces every dense contraction the reference delegates to lazyten/BLAS: the
+// orthogonalisation X^T F X and back-transformation X C' of the generalised eigensolve
+// (ScfBase.hh:291-339), the density build (FockMatrix.cc:202), S C_o / F C_o and the outer
+// products of the Pulay error (pulay_error.cc:36-43), F_prev C_o of the TODA trace
+// (TruncatedOptDampScf.hh:332), and the Q x U merges of the divide & conquer eigensolver.
+#pragma once
+#include "common.cuh"
+
+namespace gscfb {
+
+// One GEMM of a group whose sizes are only known on the device (D&C merges after deflation).
+struct GemmDesc {
+  const double* A;
+  const double* B;
+  double* C;
+  int m, n, k;
+  int lda, ldb, ldc;
+  double alpha, beta;
+};
+
+struct GemmParams {
+  const double* A;
+  const double* B;
+  double* C;
+  int m, n, k;
+  int lda, ldb, ldc;
+  long long sA, sB, sC;   // strides between batch entries (blockIdx.z)
+  int kbatch;             // C = alpha * sum_{q<kbatch} op(A_q) op(B_q) + beta*C
+  long long skA, skB;     // strides between the q slices
+  double alpha, beta;
+  const int* batch_map;   // optional: batch entry z works on problem batch_map[z]
+  const GemmDesc* descs;  // optional: grouped mode, one descriptor per blockIdx.z
+};
+
+inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A, int lda,
+                              const double* B, int ldb, double beta, double* C, int ldc) {
+  GemmParams p{};
+  p.A = A; p.B = B; p.C = C; p.m = m; p.n = n; p.k = k;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
+  p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
+  return p;
+}
+
+// Launch C = alpha op(A) op(B) + beta C for `batch` entries (grid.z).  max_m/max_n bound the
+// grid in grouped mode (device-side sizes); pass p.m/p.n otherwise.
+int launch_gemm(bool ta, bool tb, const GemmParams& p, int batch, int max_m, int max_n,
+                cudaStream_t stream);
+
+// Convenience wrappers.
+inline int gemm(bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda,
+                const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st) {
+  GemmParams p = gemm_params(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  return launch_gemm(ta, tb, p, 1, m, n, st);
+}
+inline int gemm_batched(bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
+                        int lda, long long sA, const double* B, int ldb, long long sB,
+                        double beta, double* C, int ldc, long long sC, int batch,
+                        const int* batch_map, cudaStream_t st) {
+  GemmParams p = gemm_params(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  p.sA = sA; p.sB = sB; p.sC = sC; p.batch_map = batch_map;
+  return launch_gemm(ta, tb, p, batch, m, n, st);
+}
+
+}  // namespace gscfb

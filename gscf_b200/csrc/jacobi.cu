@@ -1,0 +1,200 @@
+// Batched symmetric eigensolver for small matrices (n <= 160): one CTA per matrix, the whole
+// solve in shared memory, one warp per column pair.
+//
+// Algorithm: one-sided (Hestenes) cyclic Jacobi on G = A + sigma*I.  sigma = 2 * Gershgorin
+// radius makes G positive definite with spectrum in [R, 3R], so G = U diag(lambda + sigma) U^T
+// and orthogonalising the columns of G by plane rotations (G <- G J) converges to
+// G J = U diag(lambda+sigma): column norms give the eigenvalues, normalised columns the
+// eigenvectors, both to absolute accuracy O(eps * ||A||) - what the 1e-9 / 1e-8 parity
+// targets of the SCF need.  One-sided Jacobi needs a single n x n array (128 KiB at n = 128);
+// the two-sided form needs A and V (256 KiB > 227 KiB of shared memory per CTA).
+//
+// Used for: the batched ensemble eigensolves (BASELINE config 4, n = 128), the leaves of the
+// divide & conquer tridiagonal solver, and tiny problems (reference example, n = 14).
+#include "eig.cuh"
+
+namespace gscfb {
+
+constexpr int kJacobiMaxSweeps = 40;
+
+template <int NPL>
+__global__ void __launch_bounds__(1024)
+jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long strideA,
+                       double* __restrict__ w, long long stride_w, double* __restrict__ Z,
+                       int ldz, long long strideZ, int n, const int* __restrict__ batch_map,
+                       int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  const int ne = (n + 1) & ~1;         // even number of (possibly one dummy) columns
+  const int ldg = n;                   // column stride in shared memory
+  double* G = sm;                      // ne * ldg
+  double* lam = G + (size_t)ne * ldg;  // ne
+  __shared__ double s_red[33];
+  __shared__ double s_sigma;
+
+  const long long prob = batch_map ? batch_map[blockIdx.x] : blockIdx.x;
+  const double* A = Ain + prob * strideA;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+  // ---- load the full symmetric matrix from the lower triangle; Gershgorin radius ------------
+  double rmax = 0.0;
+  for (int idx = tid; idx < ne * ldg; idx += nthr) {
+    const int c = idx / ldg, r = idx - c * ldg;
+    double v = 0.0;
+    if (c < n) v = (r >= c) ? A[(size_t)c * lda + r] : A[(size_t)r * lda + c];
+    G[idx] = v;
+  }
+  __syncthreads();
+  for (int c = tid; c < n; c += nthr) {
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += fabs(G[(size_t)c * ldg + r]);
+    rmax = fmax(rmax, s);
+  }
+  rmax = warp_max(rmax);
+  if (lane == 0) s_red[warp] = rmax;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < nwarp; ++i) m = fmax(m, s_red[i]);
+    s_sigma = (m > 0.0 && isfinite(m)) ? 2.0 * m : 1.0;
+  }
+  __syncthreads();
+  const double sigma = s_sigma;
+  for (int c = tid; c < n; c += nthr) G[(size_t)c * ldg + c] += sigma;
+  __syncthreads();
+
+  const double tol = sqrt((double)n) * 2.220446049250313e-16;
+  const int npairs = ne >> 1;
+  int sweeps = 0;
+  bool converged = false;
+  for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
+    int rotated = 0;
+    for (int step = 0; step < ne - 1; ++step) {
+      for (int pr = warp; pr < npairs; pr += nwarp) {
+        // round-robin tournament: index ne-1 is fixed, the others rotate
+        int p, q;
+        if (pr == 0) {
+          p = ne - 1;
+          q = step;
+        } else {
+          p = (step + pr) % (ne - 1);
+          q = (step - pr + (ne - 1)) % (ne - 1);
+        }
+        if (p > q) { const int t = p; p = q; q = t; }
+        double* gp = G + (size_t)p * ldg;
+        double* gq = G + (size_t)q * ldg;
+        double xp[NPL], xq[NPL];
+        double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int r = lane + 32 * i;
+          xp[i] = r < n ? gp[r] : 0.0;
+          xq[i] = r < n ? gq[r] : 0.0;
+          a = fma(xp[i], xp[i], a);
+          b = fma(xq[i], xq[i], b);
+          c = fma(xp[i], xq[i], c);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        c = warp_sum(c);
+        if (fabs(c) > tol * sqrt(a * b) && a > 0.0 && b > 0.0) {
+          rotated = 1;
+          const double zeta = (b - a) / (2.0 * c);
+          const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t);
+          const double sn = cs * t;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int r = lane + 32 * i;
+            if (r < n) {
+              gp[r] = cs * xp[i] - sn * xq[i];
+              gq[r] = sn * xp[i] + cs * xq[i];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(rotated)) {
+      converged = true;
+      ++sweeps;
+      break;
+    }
+  }
+
+  // ---- eigenvalues = column norms - sigma; normalise columns --------------------------------
+  for (int c = warp; c < n; c += nwarp) {
+    double* g = G + (size_t)c * ldg;
+    double s = 0.0;
+    for (int r = lane; r < n; r += 32) s = fma(g[r], g[r], s);
+    s = warp_sum(s);
+    const double nrm = sqrt(s);
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int r = lane; r < n; r += 32) g[r] *= inv;
+    if (lane == 0) lam[c] = nrm - sigma;
+  }
+  __syncthreads();
+
+  // ---- rank sort ascending (ties broken by index) and scatter to global ------------------------
+  double* wout = w + prob * stride_w;
+  double* Zout = Z + prob * strideZ;
+  for (int c = warp; c < n; c += nwarp) {
+    const double lc = lam[c];
+    int rank = 0;
+    for (int j = lane; j < n; j += 32) {
+      const double lj = lam[j];
+      rank += (lj < lc || (lj == lc && j < c)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0) wout[rank] = lc;
+    const double* g = G + (size_t)c * ldg;
+    for (int r = lane; r < n; r += 32) Zout[(size_t)rank * ldz + r] = g[r];
+  }
+  if (tid == 0 && info) info[prob] = converged ? 0 : 1;
+}
+
+size_t jacobi_smem_bytes(int n) {
+  const int ne = (n + 1) & ~1;
+  return ((size_t)ne * n + ne) * sizeof(double);
+}
+
+int jacobi_syev_batched(int n, const double* A, int lda, long long strideA, double* w,
+                        long long stride_w, double* Z, int ldz, long long strideZ, int batch,
+                        const int* batch_map, int* info_dev, cudaStream_t st) {
+  if (batch <= 0 || n <= 0) return GSCF_B200_OK;
+  if (n > kJacobiMaxN) {
+    set_last_error("jacobi_syev_batched: n > 160 does not fit in shared memory");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
+  const size_t smem = jacobi_smem_bytes(n);
+  const int npairs = (n + 1) / 2;
+  int warps = npairs < 32 ? npairs : 32;
+  if (warps < 1) warps = 1;
+  const int threads = warps * 32;
+#define GSCF_JACOBI_LAUNCH(NPL)                                                                  \
+  do {                                                                                           \
+    static bool cfg = false;                                                                     \
+    if (!cfg) {                                                                                  \
+      GSCF_CUDA_TRY(cudaFuncSetAttribute(jacobi_onesided_kernel<NPL>,                            \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                         (int)jacobi_smem_bytes(32 * NPL > kJacobiMaxN          \
+                                                                    ? kJacobiMaxN               \
+                                                                    : 32 * NPL)));              \
+      cfg = true;                                                                                \
+    }                                                                                            \
+    jacobi_onesided_kernel<NPL><<<batch, threads, smem, st>>>(A, lda, strideA, w, stride_w, Z,   \
+                                                              ldz, strideZ, n, batch_map,       \
+                                                              info_dev);                        \
+  } while (0)
+  if (n <= 32) GSCF_JACOBI_LAUNCH(1);
+  else if (n <= 64) GSCF_JACOBI_LAUNCH(2);
+  else if (n <= 128) GSCF_JACOBI_LAUNCH(4);
+  else GSCF_JACOBI_LAUNCH(5);
+#undef GSCF_JACOBI_LAUNCH
+  count_launch();
+  GSCF_CHECK_LAUNCH();
+  return GSCF_B200_OK;
+}
+
+}  // namespace gscfb

@@ -1,0 +1,219 @@
+"""Kernel-level parity through the C ABI against numpy on the same seeded inputs (GPU)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    from gscf_b200 import lib as L
+
+    assert torch.cuda.is_available()
+    return torch, L
+
+
+def dev(torch, a):
+    """numpy array -> device tensor holding the same bytes (flat, column-major preserved)."""
+    return torch.from_numpy(np.ascontiguousarray(a).ravel().copy()).cuda()
+
+
+def colmajor(a, ld=None):
+    """2-D numpy -> flat column-major buffer with leading dimension ld (zero padded)."""
+    m, n = a.shape
+    ld = m if ld is None else ld
+    buf = np.zeros((n, ld))
+    buf[:, :m] = a.T
+    return buf.ravel()
+
+
+def from_colmajor(buf, m, n, ld):
+    return np.asarray(buf).reshape(n, ld)[:, :m].T.copy()
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(14, 14, 2), (64, 64, 64), (129, 67, 33), (257, 300, 128), (1024, 1024, 96),
+                                   (1, 1, 1), (5, 3, 0)])
+def test_dgemm(env, ta, tb, m, n, k):
+    torch, L = env
+    rng = np.random.default_rng(m * 1000 + n * 10 + k + ta * 2 + tb)
+    A = rng.standard_normal((k, m) if ta else (m, k))
+    B = rng.standard_normal((n, k) if tb else (k, n))
+    Cm = rng.standard_normal((m, n))
+    lda = A.shape[0] + (A.shape[0] % 2) + 2
+    ldb = B.shape[0] + 3  # odd leading dimension: exercises the 8-byte cp.async path
+    ldc = m + 1
+    dA, dB, dC = dev(torch, colmajor(A, lda)), dev(torch, colmajor(B, ldb)), dev(torch, colmajor(Cm, ldc))
+    alpha, beta = 1.5, -0.25
+    L.check(L.lib.gscf_b200_dgemm(ta, tb, m, n, k, alpha, dA.data_ptr(), lda, 0, dB.data_ptr(), ldb, 0, beta,
+                                  dC.data_ptr(), ldc, 0, 1, None))
+    torch.cuda.synchronize()
+    got = from_colmajor(dC.cpu().numpy(), m, n, ldc)
+    opA = A.T if ta else A
+    opB = B.T if tb else B
+    ref = alpha * (opA @ opB) + beta * Cm
+    tol = 1e-13 * max(1, k) * (1 + np.abs(ref).max())
+    assert np.abs(got - ref).max() < tol
+
+
+def test_dgemm_batched_and_large_tile(env):
+    torch, L = env
+    rng = np.random.default_rng(7)
+    batch, m, n, k = 3, 1536, 1408, 160  # large-tile configuration (>= 120 128x128 tiles)
+    A = rng.standard_normal((batch, k, m))  # column-major m x k each
+    B = rng.standard_normal((batch, n, k))  # column-major k x n each
+    dA, dB = dev(torch, A), dev(torch, B)
+    dC = torch.zeros(batch * m * n, dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_dgemm(0, 0, m, n, k, 1.0, dA.data_ptr(), m, m * k, dB.data_ptr(), k, k * n, 0.0,
+                                  dC.data_ptr(), m, m * n, batch, None))
+    torch.cuda.synchronize()
+    got = dC.cpu().numpy().reshape(batch, n, m)
+    for b in range(batch):
+        ref = (A[b].T @ B[b].T).T  # stored column-major == transpose
+        assert np.abs(got[b] - ref).max() < 1e-11
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 14, 31, 32, 33, 64, 100, 128, 160])
+def test_syev_jacobi(env, n):
+    torch, L = env
+    rng = np.random.default_rng(n)
+    batch = 3
+    ld = n + (n % 2)
+    mats = []
+    for b in range(batch):
+        a = rng.standard_normal((n, n))
+        a = a + a.T
+        if b == 1 and n > 4:  # degenerate / clustered spectrum
+            q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            ev = np.repeat(np.arange(1, n // 2 + 2), 2)[:n].astype(float)
+            a = (q * ev) @ q.T
+            a = 0.5 * (a + a.T)
+        mats.append(a)
+    buf = np.concatenate([colmajor(np.tril(a) + 7.0 * np.triu(np.ones_like(a), 1), ld) for a in mats])
+    dA = dev(torch, buf)
+    dw = torch.zeros(batch * n, dtype=torch.float64, device="cuda")
+    dZ = torch.zeros(batch * ld * n, dtype=torch.float64, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    L.check(L.lib.gscf_b200_syev(L.EIG_JACOBI, n, dA.data_ptr(), ld, ld * n, dw.data_ptr(), n, dZ.data_ptr(), ld,
+                                 ld * n, batch, None, 0, info.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert info.cpu().numpy().tolist() == [0] * batch
+    w = dw.cpu().numpy().reshape(batch, n)
+    Z = dZ.cpu().numpy().reshape(batch, n, ld)
+    for b, a in enumerate(mats):
+        wref = np.linalg.eigvalsh(a)
+        scale = max(1.0, np.abs(wref).max())
+        assert np.abs(w[b] - wref).max() < 1e-12 * scale * max(1, n / 8)
+        z = Z[b][:, :n].T
+        assert np.abs(z.T @ z - np.eye(n)).max() < 1e-12
+        assert np.abs(a @ z - z * w[b]).max() < 2e-12 * scale * max(1, n / 8)
+
+
+def test_frob_multidot_and_axpby(env):
+    torch, L = env
+    rng = np.random.default_rng(3)
+    for (n, cols, ld, count, batch) in [(14, 14, 16, 3, 1), (127, 254, 128, 5, 2), (256, 256, 256, 9, 1),
+                                        (1024, 1024, 1024, 8, 1)]:
+        nslots = count + 1
+        ring = rng.standard_normal((batch, nslots, cols, ld))
+        enew = rng.standard_normal((batch, cols, ld))
+        slots = np.array(rng.permutation(nslots)[:count], dtype=np.int32)
+        dR, dE = dev(torch, ring), dev(torch, enew)
+        out = torch.zeros(batch * 16, dtype=torch.float64, device="cuda")
+        wsz = L.lib.gscf_b200_frob_multidot_worksize(count, n, cols, batch)
+        work = torch.zeros(max(1, wsz // 8), dtype=torch.float64, device="cuda")
+        L.check(L.lib.gscf_b200_frob_multidot(dE.data_ptr(), dR.data_ptr(), cols * ld,
+                                              slots.ctypes.data_as(C.POINTER(C.c_int)), count, n, cols, ld,
+                                              cols * ld, nslots * cols * ld, batch, out.data_ptr(), 16,
+                                              work.data_ptr(), wsz, None))
+        coeff = rng.standard_normal((batch, 16))
+        dcoef = dev(torch, coeff)
+        res = torch.zeros(batch * cols * ld, dtype=torch.float64, device="cuda")
+        L.check(L.lib.gscf_b200_axpby_n(res.data_ptr(), cols * ld, dR.data_ptr(), cols * ld, nslots * cols * ld,
+                                        slots.ctypes.data_as(C.POINTER(C.c_int)), count, dcoef.data_ptr(), 16, n, cols,
+                                        ld, batch, None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(batch, 16)
+        gres = res.cpu().numpy().reshape(batch, cols, ld)
+        for b in range(batch):
+            for j, s in enumerate(slots):
+                ref = np.sum(enew[b][:, :n] * ring[b, s][:, :n])
+                assert abs(got[b, j] - ref) < 1e-12 * n * cols
+            ref = sum(coeff[b, j] * ring[b, s][:, :n] for j, s in enumerate(slots))
+            assert np.abs(gres[b][:, :n] - ref).max() < 1e-13 * count * 10
+
+
+def test_diis_solve_matches_dgesv(env):
+    torch, L = env
+    from oracle import diis_linear_system_matrix
+
+    rng = np.random.default_rng(11)
+    M = 8
+    batch = 5
+    for k in [2, 3, 5, 8]:
+        errs = rng.standard_normal((batch, M, 40)) * np.logspace(0, -6, M)[None, :, None]
+        gram = np.einsum("bik,bjk->bij", errs, errs)
+        order = np.array(rng.permutation(M)[:k], dtype=np.int32)
+        dG = dev(torch, gram)
+        coef = torch.zeros(batch * 16, dtype=torch.float64, device="cuda")
+        fail = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        L.check(L.lib.gscf_b200_diis_solve(dG.data_ptr(), M, M * M, order.ctypes.data_as(C.POINTER(C.c_int)), k,
+                                           coef.data_ptr(), 16, fail.data_ptr(), batch, None))
+        torch.cuda.synchronize()
+        c = coef.cpu().numpy().reshape(batch, 16)
+        assert fail.cpu().numpy().sum() == 0
+        for b in range(batch):
+            ov = [[gram[b, order[i], order[i - j]] for j in range(i + 1)] for i in range(k)]
+            B = diis_linear_system_matrix(ov)
+            rhs = np.zeros(k + 1)
+            rhs[k] = -1
+            ref = np.linalg.solve(B, rhs)[:k]
+            assert np.abs(c[b, :k] - ref).max() < 1e-9 * max(1, np.abs(ref).max())
+            assert abs(c[b, :k].sum() - 1) < 1e-10
+    # singular system -> failure flag (ExcDiisStepFailed)
+    gram = np.zeros((1, M, M))
+    dG = dev(torch, gram)
+    order = np.arange(3, dtype=np.int32)
+    coef = torch.zeros(16, dtype=torch.float64, device="cuda")
+    fail = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(L.lib.gscf_b200_diis_solve(dG.data_ptr(), M, M * M, order.ctypes.data_as(C.POINTER(C.c_int)), 3,
+                                       coef.data_ptr(), 16, fail.data_ptr(), 1, None))
+    torch.cuda.synchronize()
+    assert fail.cpu().numpy()[0] == 1
+
+
+@pytest.mark.parametrize("n,o", [(14, 2), (128, 16), (200, 25)])
+def test_density_and_pulay_error(env, n, o):
+    torch, L = env
+    from oracle import pulay_error
+
+    rng = np.random.default_rng(n)
+    ld = L.lib.gscf_b200_padded_ld(n)
+    S = rng.standard_normal((n, n)); S = S @ S.T / n + np.eye(n)
+    F = rng.standard_normal((n, n)); F = F + F.T
+    Cm = rng.standard_normal((n, n))
+    dS, dF, dC = dev(torch, colmajor(S, ld)), dev(torch, colmajor(F, ld)), dev(torch, colmajor(Cm, ld))
+    dD = torch.zeros(ld * n, dtype=torch.float64, device="cuda")
+    dE = torch.zeros(ld * n, dtype=torch.float64, device="cuda")
+    wsz = L.lib.gscf_b200_pulay_error_worksize(n, o, 1)
+    work = torch.zeros(wsz // 8, dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_density(n, o, dC.data_ptr(), ld, 0, dD.data_ptr(), ld, 0, 1, None))
+    L.check(L.lib.gscf_b200_pulay_error(n, o, 2.0, dS.data_ptr(), ld, 0, dF.data_ptr(), ld, 0, dC.data_ptr(), ld, 0,
+                                        dE.data_ptr(), ld, 0, work.data_ptr(), 0, 1, None))
+    torch.cuda.synchronize()
+    D = from_colmajor(dD.cpu().numpy(), n, n, ld)
+    E = from_colmajor(dE.cpu().numpy(), n, n, ld)
+    assert np.abs(D - Cm[:, :o] @ Cm[:, :o].T).max() < 1e-12 * o
+    ref = pulay_error(F[None], Cm[None], S, o, o)[0]
+    assert np.abs(E - ref).max() < 1e-11 * np.abs(ref).max()
+
+
+def test_measure_peaks_runs(env):
+    torch, L = env
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    L.check(L.lib.gscf_b200_measure_peaks(C.byref(a), C.byref(b), C.byref(c)))
+    assert a.value > 1.0 and b.value > 1.0 and c.value > 500.0

@@ -1,0 +1,237 @@
+"""SCF-level parity of the CUDA path against the oracle and the reference's golden vectors.
+
+Mirrors tests/FunctionalityTest.cc of the reference (same problem, same checks, same bounds)
+and adds the north_star parity gate on synthetic problems: identical n_iter, |dE| <= 1e-10,
+max|d eps| <= 1e-9, ||dD||_F <= 1e-8.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_E, TOL_EPS, TOL_D = 1e-10, 1e-9, 1e-8
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+
+    assert torch.cuda.is_available()
+    import gscf_b200
+
+    return gscf_b200
+
+
+def _oracle_mock(k_exp, guess, which):
+    from oracle import plain_scf, pulay_diis_scf, truncated_opt_damp_scf
+    from oracle.mock_fock import IntegralsSturmian14, MockFockProblem
+
+    prob = MockFockProblem(IntegralsSturmian14(4.0, k_exp), 2, 2)
+    F0, e1, e2 = prob.fock(guess)
+    fn = {"plain": plain_scf, "diis": pulay_diis_scf, "toda": truncated_opt_damp_scf}[which]
+    return fn(prob, F0, e1, e2)
+
+
+@pytest.mark.parametrize("which", ["plain", "diis", "toda"])
+def test_functionality_like_reference(G, which):
+    """tests/FunctionalityTest.cc:34-195 through the GPU solvers (host Fock plugin)."""
+    from helpers import GOLD, Sturmian14Fock, adjust_phase, functionality_guess
+
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], GOLD["n_alpha"], GOLD["n_beta"], functionality_guess())
+    # the reference test passes the unknown key "n_prev_steps": it must be ignored
+    scf = {"plain": G.PlainScf, "diis": G.PulayDiisScf, "toda": G.TruncatedOptDampScf}[which]({"n_prev_steps": 4})
+    res = scf.solve(fock, fock.s_bb)
+    basetol = GOLD["basetol"]
+    assert res.n_iter() < GOLD["n_iter_bound"][which]
+    ev = res.eigensolution().evalues()
+    np.testing.assert_allclose(ev, GOLD["eval_expected"], atol=2 * basetol, rtol=0)
+    evec = res.eigensolution().evectors()
+    ref = np.array(GOLD["evec_expected_rows"])
+    for i in range(GOLD["n_alpha"]):
+        np.testing.assert_allclose(adjust_phase(evec[:, i], ref[:, i]), ref[:, i], atol=10 * basetol, rtol=0)
+    en = res.problem_matrix().energies
+    assert abs(en["energy_1e_terms"] - GOLD["exp_energy_1e_terms"]) < basetol
+    assert abs(en["energy_coulomb"] - GOLD["exp_energy_coulomb"]) < basetol
+    assert abs(en["energy_exchange"] - GOLD["exp_energy_exchange"]) < basetol
+    assert abs(en["energy_total"] - GOLD["exp_energy_total"]) < basetol
+    # parity with the oracle: same iteration count, energies to 1e-10, per-iteration trace
+    o = _oracle_mock(GOLD["k_exp"], functionality_guess(), which)
+    assert res.n_iter() == o.n_iter
+    assert abs(res.energy_total - o.energy_total) < TOL_E
+    assert np.abs(ev - o.orben[0]).max() < TOL_EPS
+    np.testing.assert_allclose(res.trace_error, o.trace_error, rtol=1e-6, atol=1e-13)
+    np.testing.assert_allclose(res.trace_energy, o.trace_energy, rtol=0, atol=1e-10)
+    D = res.density[0]
+    assert np.linalg.norm(D - o.density(2, 2)[0]) < TOL_D
+    if which == "diis":
+        for a, b in zip(res.trace_coeff, o.trace_coeff):
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9)
+        assert len(res.diis_coefficients) == 4
+        # overlap vectors newest-first (PulayDiisScf.hh:62-81)
+        assert [len(v) for v in res.error_overlaps] == [1, 2, 3, 4]
+
+
+def test_example_config1(G):
+    """BASELINE configs[0]: examples/hartree_fock (k=1.351, Loewdin guess): 11 / 6 / 11 iterations."""
+    from helpers import Sturmian14Fock
+    from oracle.mock_fock import loewdin_guess
+
+    d = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "sturmian14.npz"))
+    guess = loewdin_guess(d["s_bb"])
+    its = {}
+    for which, cls in [("plain", G.PlainScf), ("diis", G.PulayDiisScf), ("toda", G.TruncatedOptDampScf)]:
+        fock = Sturmian14Fock(4.0, 1.351, 2, 2, guess)
+        res = cls().solve(fock, fock.s_bb)
+        o = _oracle_mock(1.351, guess, which)
+        its[which] = res.n_iter()
+        assert res.n_iter() == o.n_iter
+        assert abs(res.energy_total - o.energy_total) < TOL_E
+        assert abs(res.energy_total - (-13.194204539338)) < 1e-9
+    assert its == {"plain": 11, "diis": 6, "toda": 11}
+
+
+def test_hooks_and_custom_error(G):
+    """Virtual hooks (ScfLibrary.hh:41-100) and a calculate_error override (ErrorWrapped)."""
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+    from oracle import pulay_error
+
+    calls = []
+
+    class Verbose(G.PulayDiisScf):
+        def before_iteration_step(self, s):
+            calls.append(("before", s.n_iter()))
+
+        def on_update_eigenpairs(self, s):
+            calls.append(("eig", s.n_iter(), float(s.eigensolution().evalues()[0])))
+
+        def on_new_diagmat(self, s):
+            calls.append(("diag", s.n_iter(), s.diagonalised_matrix().shape))
+
+        def after_iteration_step(self, s):
+            calls.append(("after", s.n_iter(), s.last_error_norm))
+
+        def calculate_error(self, state, F, Cm, orben):
+            return pulay_error(F, Cm, state.overlap_matrix(), 2, 2)
+
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    res = Verbose().solve(fock, fock.s_bb)
+    assert res.n_iter() == 6
+    assert [c[0] for c in calls[:4]] == ["before", "diag", "eig", "after"]
+    assert calls[-1][0] == "after" and calls[-1][2] < 5e-7
+    assert sum(1 for c in calls if c[0] == "before") == 6
+
+
+def test_max_iter_and_control_params(G):
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    scf = G.PlainScf({"max_iter": 3})
+    with pytest.raises(G.ExcMaximumNumberOfIterationsReached) as ei:
+        scf.solve(fock, fock.s_bb)
+    assert ei.value.state.is_failed() and ei.value.state.n_iter() == 3
+    m = G.GenMap()
+    G.PulayDiisScf({"diis_n_prev_steps": 7, "max_error_norm": 1e-9}).get_control_params(m)
+    assert m["diis_n_prev_steps"] == 7 and m["max_error_norm"] == 1e-9 and m["max_iter"] == 100
+    # looser threshold converges earlier (convergence tested before each step on the previous error)
+    res = G.PlainScf({"max_error_norm": 1e-3}).solve(
+        Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess()), fock.s_bb)
+    assert res.n_iter() == 6  # oracle trace: ||e|| = 5.26e-4 after iteration 6
+
+
+def _run_synthetic(G, n, o, aux, which, seed=0, params=None, n_beta=None, eig=0):
+    from gscf_b200 import lib as L
+
+    fock = G.DeviceDFFock(n, o, n_beta, n_aux=aux, seeds=[seed])
+    eng, st = G.solve_device_problem(fock, which, params, eig_method=eig)
+    try:
+        assert st == L.OK, L.last_error()
+        out = dict(n_iter=int(eng.n_iter()[0]), e=eng.energies(), w=eng.orben()[0], D=eng.get_matrix("density")[0],
+                   err=float(eng.error_norm()[0]), trace=eng.trace(0))
+    finally:
+        eng.close()
+        fock.close()
+    return out
+
+
+def _oracle_synthetic(n, o, aux, which, seed=0, n_beta=None, **kw):
+    from oracle import plain_scf, pulay_diis_scf, truncated_opt_damp_scf
+    from oracle.synthetic import SyntheticDFProblem
+
+    p = SyntheticDFProblem(n, o, n_beta, n_aux=aux, seed=seed)
+    C0 = p.core_guess()
+    C0 = np.stack([C0, C0]) if p.unrestricted else C0[None]
+    F0, e1, e2 = p.fock(C0)
+    fn = {"plain": plain_scf, "diis": pulay_diis_scf, "toda": truncated_opt_damp_scf}[which]
+    return fn(p, F0, e1, e2, **kw), p
+
+
+@pytest.mark.parametrize("n,o,aux,which,kw", [
+    (64, 8, 8, "diis", dict(n_prev_steps=4)),
+    (128, 16, 16, "diis", dict(n_prev_steps=8)),
+    (128, 16, 8, "diis", dict(n_prev_steps=4)),   # 13 iterations: ring eviction exercised
+    (128, 16, 16, "toda", dict()),                # damped branch (lambda < 1) and the flip rule
+    (100, 13, 7, "toda", dict()),
+])
+def test_synthetic_parity_small(G, n, o, aux, which, kw):
+    params = {}
+    if "n_prev_steps" in kw:
+        params["diis_n_prev_steps"] = kw["n_prev_steps"]
+    got = _run_synthetic(G, n, o, aux, which, params=params)
+    ref, p = _oracle_synthetic(n, o, aux, which, **kw)
+    assert got["n_iter"] == ref.n_iter
+    assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
+    assert np.abs(got["w"][0] - ref.orben[0]).max() < TOL_EPS
+    assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < TOL_D
+    np.testing.assert_allclose(got["trace"][1], ref.trace_error, rtol=1e-5, atol=1e-12)
+    if which == "toda":
+        lam = [float(c[0]) for c in got["trace"][2]]
+        np.testing.assert_allclose(lam, ref.trace_coeff, rtol=1e-6, atol=1e-9)
+        assert min(lam) < 0.9  # the damped branch really ran
+
+
+def test_synthetic_unrestricted(G):
+    n, na, nb, aux = 64, 8, 6, 8
+    got = _run_synthetic(G, n, na, aux, "diis", seed=3, n_beta=nb)
+    ref, p = _oracle_synthetic(n, na, aux, "diis", seed=3, n_beta=nb)
+    assert got["n_iter"] == ref.n_iter
+    assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
+    assert np.abs(got["w"] - ref.orben).max() < TOL_EPS
+    Dref = ref.density(na, nb)
+    assert np.linalg.norm(got["D"] - Dref) < TOL_D
+    gt = _run_synthetic(G, n, na, aux, "toda", seed=3, n_beta=nb)
+    rt, _ = _oracle_synthetic(n, na, aux, "toda", seed=3, n_beta=nb)
+    assert gt["n_iter"] == rt.n_iter
+    assert abs(gt["e"][0][0] + gt["e"][1][0] - rt.energy_total) < TOL_E
+
+
+def test_ensemble_lockstep(G):
+    """Batched ensemble (config 4 in miniature): every member equals its single-problem oracle."""
+    from gscf_b200 import lib as L
+
+    n, o, aux, P = 32, 4, 4, 24
+    seeds = list(range(100, 100 + P))
+    fock = G.DeviceDFFock(n, o, n_aux=aux, seeds=seeds)
+    eng, st = G.solve_device_problem(fock, "diis", {"diis_n_prev_steps": 4, "max_iter": 60})
+    try:
+        its = eng.n_iter()
+        e1, e2 = eng.energies()
+        conv = eng.converged()
+        w = eng.orben()
+    finally:
+        eng.close()
+        fock.close()
+    n_checked = 0
+    for i, s in enumerate(seeds):
+        from oracle import ScfFailed
+        try:
+            ref, _ = _oracle_synthetic(n, o, aux, "diis", seed=s, n_prev_steps=4, max_iter=60)
+        except ScfFailed:
+            assert conv[i] == 0
+            continue
+        assert conv[i] == 1
+        assert its[i] == ref.n_iter, (i, its[i], ref.n_iter)
+        assert abs(e1[i] + e2[i] - ref.energy_total) < TOL_E
+        assert np.abs(w[i, 0] - ref.orben[0]).max() < TOL_EPS
+        n_checked += 1
+    assert n_checked >= P // 2
+    assert len(set(its.tolist())) > 1  # members really stop at different iterations
