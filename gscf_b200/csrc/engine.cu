@@ -157,7 +157,14 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
   Span sp(e, PH_EIG);
   const int n = e->n, ld = e->ld;
   const int nm = nact * e->nblk;
-  e->cur = 1 - e->cur;  // push_new_eigensolution: current -> previous (ScfStateBase.hh:280-289)
+  // push_new_eigensolution: current -> previous (ScfStateBase.hh:280-289).  A copy restricted to
+  // the active problems (not a pointer swap): converged ensemble members keep their final C.
+  if (e->have_coeff) {
+    GSCF_TRY(scale_copy(e->Cprev(), ld, e->pstride, e->Ccur(), ld, e->pstride, 1.0, n, n * e->nblk, nact,
+                        e->act_p, e->stream));
+    GSCF_TRY(scale_copy(e->orben_prev(), n * e->nblk, (long long)n * e->nblk, e->orben_cur(), n * e->nblk,
+                        (long long)n * e->nblk, 1.0, n * e->nblk, 1, nact, e->act_p, e->stream));
+  }
   // matrix-level strides: Fd may live in the ring (problem stride != nblk*mstride); handle per block
   for (int b = 0; b < e->nblk; ++b) {
     // T = Fd * X
