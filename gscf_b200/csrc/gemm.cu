@@ -203,7 +203,7 @@ template <bool TA, bool TB>
 static int launch_t(const GemmParams& p, int batch, int max_m, int max_n, cudaStream_t st) {
   // Large tiles once the grid still covers the 148 SMs; small tiles otherwise.
   const long long big_tiles = (long long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * batch;
-  if (big_tiles >= 120 && p.descs == nullptr)
+  if (big_tiles >= 120)
     return launch_cfg<128, 128, 16, 64, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
   return launch_cfg<64, 64, 16, 32, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
 }

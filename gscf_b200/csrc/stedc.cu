@@ -1,0 +1,474 @@
+// Divide & conquer eigensolver for symmetric tridiagonal matrices on the GPU (Cuppen's method with
+// Gu-Eisenstat stabilisation - the dstedc algorithm family), batched over matrices and over the
+// merges of one tree level.
+//
+// The tree is balanced: 2^L leaves with boundaries bnd(i) = floor(i n / 2^L); all merges of a
+// level have (almost) the same size and run in the same launches.  Per level:
+//   dc_prepare   one CTA per merge: z vector, sort, deflation (dc_core.hpp, in shared memory),
+//                column typing, Givens rotations of near-degenerate pairs
+//   dc_secular   one thread per root of the secular equation; writes delta(j,i) = d_j - lam_i
+//   dc_zhat      one warp per pole: Gu-Eisenstat recomputation of z
+//   dc_vectors   eigenvectors of the rank-one problem, rows grouped by column type
+//   dc_gather    non-deflated columns -> Gq, deflated columns/eigenvalues -> output; GEMM descriptors
+//   grouped DMMA GEMM  Q_top * U_top and Q_bot * U_bot with device-side sizes (after deflation)
+// Leaves are solved by the shared-memory Jacobi kernel (jacobi.cu).
+#include "stedc.cuh"
+
+#include "dc_core.hpp"
+#include "eig.cuh"
+
+namespace gscfb {
+
+namespace {
+
+constexpr int kLeaf = 64;  // maximum leaf order
+
+__host__ __device__ inline int bnd(int i, int n, int L) { return (int)(((long long)i * n) >> L); }
+
+struct NodeGeom {
+  int lo, mid, hi;
+};
+__device__ inline NodeGeom node_geom(int t, int h, int n, int L) {
+  NodeGeom g;
+  g.lo = bnd(t << h, n, L);
+  g.mid = bnd((t << h) + (1 << (h - 1)), n, L);
+  g.hi = bnd((t + 1) << h, n, L);
+  return g;
+}
+
+// ---- leaves ------------------------------------------------------------------------------------------
+__global__ void dc_split_kernel(const double* __restrict__ d, const double* __restrict__ e, long long dstride,
+                                StedcWs ws, const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const int n = ws.n, L = ws.L;
+  const double* dq = d + q * dstride;
+  const double* eq = e + q * dstride;
+  double* dm = ws.dmod + q * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double v = dq[i];
+    // every leaf boundary b (0 < b < n) is a split point of exactly one merge: subtract |e_{b-1}|
+    // from d[b-1] and d[b]
+    // i == b - 1  <=> i + 1 is a boundary;  i == b <=> i is a boundary
+    for (int s = 1; s < (1 << L); ++s) {
+      const int b = bnd(s, n, L);
+      if (b == i + 1 || b == i) v -= fabs(eq[b - 1]);
+    }
+    dm[i] = v;
+  }
+}
+
+__global__ void dc_leaf_build_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
+                                     const int* __restrict__ map) {
+  const int leaf = blockIdx.x, zb = blockIdx.y;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n, L = ws.L, lm = ws.lmax;
+  const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
+  const double* dm = ws.dmod + q * n;
+  const double* eq = e + q * dstride;
+  double* A = ws.leafA + ((size_t)zb * ws.nleaf + leaf) * lm * lm;
+  for (int idx = threadIdx.x; idx < lm * lm; idx += blockDim.x) {
+    const int c = idx / lm, r = idx - c * lm;
+    double v = 0.0;
+    if (r == c) v = r < m ? dm[lo + r] : dm[lo];  // padding: decoupled diagonal entry
+    else if (r == c + 1 && r < m) v = eq[lo + c];
+    A[idx] = v;
+  }
+}
+
+// Place the leaf eigenvectors into the block diagonal of Z0 and the eigenvalues into lam[0],
+// dropping the eigenpair of the padding entry (its vector is exactly e_last).
+__global__ void dc_leaf_scatter_kernel(StedcWs ws, double* __restrict__ Z0, int ldz, long long sZ,
+                                       const int* __restrict__ map) {
+  const int leaf = blockIdx.x, zb = blockIdx.y;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n, L = ws.L, lm = ws.lmax;
+  const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
+  const double* Zl = ws.leafZ + ((size_t)zb * ws.nleaf + leaf) * lm * lm;
+  const double* Wl = ws.leafW + ((size_t)zb * ws.nleaf + leaf) * lm;
+  double* Zq = Z0 + q * sZ;
+  double* lam = ws.lam[0] + q * n;
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) {
+    int skip = -1;
+    if (m < lm)
+      for (int j = 0; j < lm; ++j)
+        if (Zl[(size_t)j * lm + (lm - 1)] != 0.0) { skip = j; break; }
+    s_skip = skip;
+  }
+  __syncthreads();
+  const int skip = s_skip;
+  for (int idx = threadIdx.x; idx < m * lm; idx += blockDim.x) {
+    const int jsrc = idx / m, r = idx - jsrc * m;
+    if (jsrc == skip || jsrc >= lm) continue;
+    const int jdst = (skip >= 0 && jsrc > skip) ? jsrc - 1 : jsrc;
+    if (jdst >= m) continue;
+    Zq[(size_t)(lo + jdst) * ldz + lo + r] = Zl[(size_t)jsrc * lm + r];
+    if (r == 0) lam[lo + jdst] = Wl[jsrc];
+  }
+}
+
+__global__ void zero_matrix_kernel(double* __restrict__ Z, int ldz, long long sZ, int n,
+                                   const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  double* Zq = Z + q * sZ;
+  const long long total = (long long)n * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n), r = (int)(i - (long long)c * n);
+    Zq[(size_t)c * ldz + r] = 0.0;
+  }
+}
+
+// ---- merge: prepare / deflate ------------------------------------------------------------------------
+// dynamic shared memory: k * (4 doubles + 4 ints) when it fits, otherwise the global work arrays
+__global__ void __launch_bounds__(256)
+dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, int h, int lev_in,
+                  double* __restrict__ Zin, int ldin, long long sin, int use_smem,
+                  const int* __restrict__ map) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int t = blockIdx.x, zb = blockIdx.y;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n, L = ws.L;
+  const NodeGeom g = node_geom(t, h, n, L);
+  const int lo = g.lo, n1 = g.mid - g.lo, k = g.hi - g.lo;
+  double* Zq = Zin + q * sin;
+  const double* lam_in = ws.lam[lev_in] + q * n + lo;
+  double *sd, *sz, *sdl, *sw;
+  int *sidx, *sct, *snd, *sdc;
+  if (use_smem) {
+    sd = reinterpret_cast<double*>(smraw);
+    sz = sd + k; sdl = sz + k; sw = sdl + k;
+    sidx = reinterpret_cast<int*>(sw + k);
+    sct = sidx + k; snd = sct + k; sdc = snd + k;
+  } else {
+    sd = ws.dwork + q * n + lo; sz = ws.z + q * n + lo; sdl = ws.dlamda + q * n + lo; sw = ws.w + q * n + lo;
+    sidx = ws.idx + q * n + lo; sct = ws.ctype + q * n + lo; snd = ws.ndcol + q * n + lo; sdc = ws.dcol + q * n + lo;
+  }
+  const double ecoup = (e + q * dstride)[g.mid - 1];
+  const double sgn = ecoup < 0.0 ? -1.0 : 1.0;
+  const double rho = 2.0 * fabs(ecoup);
+  const double rs2 = 0.70710678118654752440;  // 1/sqrt(2)
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    sd[j] = lam_in[j];
+    const double zz = j < n1 ? Zq[(size_t)(lo + j) * ldin + (g.mid - 1)] : sgn * Zq[(size_t)(lo + j) * ldin + g.mid];
+    sz[j] = zz * rs2;
+    sct[j] = j < n1 ? 1 : 3;
+  }
+  __syncthreads();
+  // rank sort (ties by index) -> idx
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const double dj = sd[j];
+    int r = 0;
+    for (int i = 0; i < k; ++i) {
+      const double di = sd[i];
+      r += (di < dj || (di == dj && i < j)) ? 1 : 0;
+    }
+    sidx[r] = j;
+  }
+  __syncthreads();
+  __shared__ int s_K, s_nrot, s_c[4];
+  int* meta = ws.meta + ((size_t)q * ws.nleaf + t) * 8;
+  int* gpos = ws.gpos + q * n + lo;
+  int* rot_a = ws.rot_a + q * n + lo;
+  int* rot_b = ws.rot_b + q * n + lo;
+  double* rot_c = ws.rot_c + q * n + lo;
+  double* rot_s = ws.rot_s + q * n + lo;
+  if (threadIdx.x == 0) {
+    int K = 0, nrot = 0;
+    dc_deflate(k, sd, sz, rho, sidx, sct, &K, sdl, sw, snd, sdc, &nrot, rot_a, rot_b, rot_c, rot_s);
+    // group the poles by column type: [1 | 2 | 3]
+    int c1 = 0, c2 = 0, c3 = 0;
+    for (int p = 0; p < K; ++p) {
+      const int ty = sct[snd[p]];
+      c1 += ty == 1; c2 += ty == 2; c3 += ty == 3;
+    }
+    int o1 = 0, o2 = c1, o3 = c1 + c2;
+    for (int p = 0; p < K; ++p) {
+      const int ty = sct[snd[p]];
+      gpos[p] = ty == 1 ? o1++ : (ty == 2 ? o2++ : o3++);
+    }
+    s_K = K; s_nrot = nrot; s_c[0] = c1; s_c[1] = c2; s_c[2] = c3;
+    meta[0] = K; meta[1] = nrot; meta[2] = c1; meta[3] = c2; meta[4] = c3;
+    (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
+  }
+  __syncthreads();
+  const int K = s_K, nrot = s_nrot;
+  if (use_smem) {
+    double* gd = ws.dwork + q * n + lo;
+    double* gdl = ws.dlamda + q * n + lo;
+    double* gw = ws.w + q * n + lo;
+    int* gnd = ws.ndcol + q * n + lo;
+    int* gdc = ws.dcol + q * n + lo;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      gd[j] = sd[j];
+      if (j < K) { gdl[j] = sdl[j]; gw[j] = sw[j]; gnd[j] = snd[j]; }
+      if (j < k - K) gdc[j] = sdc[j];
+    }
+  }
+  // Givens rotations of the deflated near-degenerate pairs, in order
+  for (int r = 0; r < nrot; ++r) {
+    const int a = rot_a[r], b = rot_b[r];
+    const double c = rot_c[r], s = rot_s[r];
+    double* x = Zq + (size_t)(lo + a) * ldin + lo;
+    double* y = Zq + (size_t)(lo + b) * ldin + lo;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      const double xv = x[i], yv = y[i];
+      x[i] = c * xv + s * yv;
+      y[i] = c * yv - s * xv;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- merge: secular equation --------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+dc_secular_kernel(StedcWs ws, int h, int lev_out, const int* __restrict__ map) {
+  const int t = blockIdx.y, zb = blockIdx.z;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n;
+  const NodeGeom g = node_geom(t, h, n, ws.L);
+  const int lo = g.lo;
+  const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double rho = (ws.rho + (size_t)q * ws.nleaf)[t];
+  double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;  // node block, [j*ld + i]
+  const double lam = secular_root(K, i, ws.dlamda + q * n + lo, ws.w + q * n + lo, rho, S + i, ws.ld, nullptr);
+  (ws.lam[lev_out] + q * n + lo)[i] = lam;
+}
+
+// zhat_j = sign(w_j) sqrt( - delta(j,j) * prod_{i != j} delta(j,i) / (d_j - d_i) )
+__global__ void __launch_bounds__(256)
+dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
+  const int t = blockIdx.y, zb = blockIdx.z;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n;
+  const NodeGeom g = node_geom(t, h, n, ws.L);
+  const int lo = g.lo;
+  const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (j >= K) return;
+  const double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
+  const double* dl = ws.dlamda + q * n + lo;
+  const double dj = dl[j];
+  double p = 1.0;
+  for (int i = lane; i < K; i += 32) {
+    const double del = S[(size_t)j * ws.ld + i];
+    p *= (i == j) ? del : del / (dj - dl[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
+  if (lane == 0) (ws.zhat + q * n + lo)[j] = copysign(sqrt(fabs(p)), (ws.w + q * n + lo)[j]);
+}
+
+// U^T[gpos[j]][i] = zhat_j / delta(j,i) / ||.||   (thread per eigenvector i)
+__global__ void __launch_bounds__(128)
+dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
+  const int t = blockIdx.y, zb = blockIdx.z;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n;
+  const NodeGeom g = node_geom(t, h, n, ws.L);
+  const int lo = g.lo;
+  const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
+  double* U = ws.U + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
+  const double* zh = ws.zhat + q * n + lo;
+  const int* gpos = ws.gpos + q * n + lo;
+  double nrm = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const double u = zh[j] / S[(size_t)j * ws.ld + i];
+    nrm = fma(u, u, nrm);
+  }
+  const double inv = 1.0 / sqrt(nrm);
+  for (int j = 0; j < K; ++j) U[(size_t)gpos[j] * ws.ld + i] = zh[j] / S[(size_t)j * ws.ld + i] * inv;
+}
+
+// Gather non-deflated columns (grouped by type) into Gq, copy deflated columns/eigenvalues to the
+// output, and write the two GEMM descriptors of this merge.
+__global__ void __launch_bounds__(128)
+dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin, int ldin, long long sin,
+                 double* __restrict__ Zout, int ldout, long long sout, int nodes, const int* __restrict__ map) {
+  const int t = blockIdx.y, zb = blockIdx.z;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n;
+  const NodeGeom g = node_geom(t, h, n, ws.L);
+  const int lo = g.lo, n1 = g.mid - g.lo, k = g.hi - g.lo;
+  const int* meta = ws.meta + ((size_t)q * ws.nleaf + t) * 8;
+  const int K = meta[0];
+  const double* Zq = Zin + q * sin;
+  double* Zo = Zout + q * sout;
+  double* Gq = ws.Gq + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int c1 = meta[2], c2 = meta[3], c3 = meta[4];
+    GemmDesc* dsc = ws.descs + ((size_t)zb * nodes + t) * 2;
+    const double* U = ws.U + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
+    GemmDesc top, bot;
+    top.A = Gq; top.lda = ws.ld; top.B = U; top.ldb = ws.ld;
+    top.C = Zo + (size_t)lo * ldout + lo; top.ldc = ldout;
+    top.m = n1; top.n = K; top.k = c1 + c2; top.alpha = 1.0; top.beta = 0.0;
+    bot.A = Gq + (size_t)c1 * ws.ld + n1; bot.lda = ws.ld; bot.B = U + (size_t)c1 * ws.ld; bot.ldb = ws.ld;
+    bot.C = Zo + (size_t)lo * ldout + lo + n1; bot.ldc = ldout;
+    bot.m = k - n1; bot.n = K; bot.k = c2 + c3; bot.alpha = 1.0; bot.beta = 0.0;
+    dsc[0] = top;
+    dsc[1] = bot;
+  }
+  const int c = blockIdx.x;
+  if (c >= k) return;
+  if (c < K) {
+    const int src = (ws.ndcol + q * n + lo)[c];
+    const int dst = (ws.gpos + q * n + lo)[c];
+    const double* x = Zq + (size_t)(lo + src) * ldin + lo;
+    double* y = Gq + (size_t)dst * ws.ld;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = x[i];
+  } else {
+    const int tdx = c - K;
+    const int src = (ws.dcol + q * n + lo)[tdx];
+    const double* x = Zq + (size_t)(lo + src) * ldin + lo;
+    double* y = Zo + (size_t)(lo + c) * ldout + lo;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = x[i];
+    if (threadIdx.x == 0) (ws.lam[lev_out] + q * n + lo)[c] = (ws.dwork + q * n + lo)[src];
+  }
+}
+
+// ---- final ascending sort -----------------------------------------------------------------------------
+__global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const int n = ws.n;
+  const double* lam = ws.lam[lev] + q * n;
+  int* rank = ws.rank + q * n;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const double lj = lam[j];
+    int r = 0;
+    for (int i = 0; i < n; ++i) {
+      const double li = lam[i];
+      r += (li < lj || (li == lj && i < j)) ? 1 : 0;
+    }
+    rank[j] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && info) info[q] = 0;
+}
+
+__global__ void dc_permute_kernel(StedcWs ws, int lev, const double* __restrict__ Zin, int ldin, long long sin,
+                                  double* __restrict__ Zout, int ldout, long long sout, double* __restrict__ w,
+                                  long long stride_w, int* __restrict__ info, const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const int n = ws.n;
+  const int j = blockIdx.x;
+  const int r = (ws.rank + q * n)[j];
+  const double* x = Zin + q * sin + (size_t)j * ldin;
+  double* y = Zout + q * sout + (size_t)r * ldout;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
+  if (threadIdx.x == 0) {
+    const double l = (ws.lam[lev] + q * n)[j];
+    (w + q * stride_w)[r] = l;
+    if (!isfinite(l) && info) info[q] = 1;
+  }
+}
+
+}  // namespace
+
+size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = up(offset);
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off = up(off + bytes);
+    return p;
+  };
+  ws.n = n; ws.ld = padded_ld(n); ws.cap = cap;
+  int L = 0;
+  while (ceil_div(n, 1 << L) > kLeaf) ++L;
+  ws.L = L; ws.nleaf = 1 << L;
+  ws.lmax = ceil_div(n, 1 << L);
+  const size_t cn = (size_t)cap * n;
+  ws.lam[0] = (double*)take(cn * 8); ws.lam[1] = (double*)take(cn * 8);
+  ws.dmod = (double*)take(cn * 8); ws.dwork = (double*)take(cn * 8); ws.z = (double*)take(cn * 8);
+  ws.dlamda = (double*)take(cn * 8); ws.w = (double*)take(cn * 8); ws.zhat = (double*)take(cn * 8);
+  ws.rot_c = (double*)take(cn * 8); ws.rot_s = (double*)take(cn * 8);
+  ws.rho = (double*)take((size_t)cap * ws.nleaf * 8);
+  ws.idx = (int*)take(cn * 4); ws.ctype = (int*)take(cn * 4); ws.ndcol = (int*)take(cn * 4);
+  ws.dcol = (int*)take(cn * 4); ws.gpos = (int*)take(cn * 4); ws.rot_a = (int*)take(cn * 4);
+  ws.rot_b = (int*)take(cn * 4); ws.rank = (int*)take(cn * 4);
+  ws.meta = (int*)take((size_t)cap * ws.nleaf * 8 * 4);
+  const size_t mat = (size_t)cap * ws.ld * n * 8;
+  if (L > 0) {
+    ws.Zb = (double*)take(mat); ws.S = (double*)take(mat); ws.U = (double*)take(mat); ws.Gq = (double*)take(mat);
+  } else {
+    ws.Zb = ws.S = ws.U = ws.Gq = nullptr;
+    ws.Zb = (double*)take(mat);
+  }
+  const size_t lsz = (size_t)cap * ws.nleaf * ws.lmax * ws.lmax * 8;
+  ws.leafA = (double*)take(lsz); ws.leafZ = (double*)take(lsz);
+  ws.leafW = (double*)take((size_t)cap * ws.nleaf * ws.lmax * 8);
+  ws.descs = (GemmDesc*)take((size_t)cap * ws.nleaf * sizeof(GemmDesc));
+  return off;
+}
+
+int stedc_batched(int n, const double* d, const double* e, long long dstride, double* w, long long stride_w,
+                  double* Z, int ldz, long long strideZ, const StedcWs& ws, int batch, const int* map,
+                  int* info_dev, cudaStream_t st) {
+  if (batch <= 0) return GSCF_B200_OK;
+  const int L = ws.L, lm = ws.lmax;
+  const int gx = std::max(1, std::min(148 * 4 / std::max(1, batch), ceil_div(n * n, 256 * 8)));
+  // buffers: X_0 (leaf eigenvectors) -> level 1 -> ... -> X_L -> sorted into Z
+  // X_L must be the workspace buffer, so X_0 = Zb for even L and Z for odd L.
+  double* bufp[2]; int bufld[2]; long long bufs[2];
+  const int first = (L % 2 == 0) ? 1 : 0;  // index 0 = user Z, 1 = Zb
+  bufp[0] = Z; bufld[0] = ldz; bufs[0] = strideZ;
+  bufp[1] = ws.Zb; bufld[1] = ws.ld; bufs[1] = (long long)ws.ld * n;
+  int cur = first;
+  // ---- leaves -----------------------------------------------------------------------------------------
+  dc_split_kernel<<<dim3(std::max(1, ceil_div(n, 256)), batch), 256, 0, st>>>(d, e, dstride, ws, map);
+  dc_leaf_build_kernel<<<dim3(ws.nleaf, batch), 256, 0, st>>>(e, dstride, ws, map);
+  count_launch(2);
+  GSCF_CHECK_LAUNCH();
+  GSCF_TRY(jacobi_syev_batched(lm, ws.leafA, lm, (long long)lm * lm, ws.leafW, lm, ws.leafZ, lm, (long long)lm * lm,
+                               ws.nleaf * batch, nullptr, nullptr, st));
+  zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[cur], bufld[cur], bufs[cur], n, map);
+  dc_leaf_scatter_kernel<<<dim3(ws.nleaf, batch), 256, 0, st>>>(ws, bufp[cur], bufld[cur], bufs[cur], map);
+  count_launch(2);
+  GSCF_CHECK_LAUNCH();
+  int lev = 0;
+  static bool cfg = false;
+  if (!cfg) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cfg = true;
+  }
+  // ---- merges -----------------------------------------------------------------------------------------
+  for (int h = 1; h <= L; ++h) {
+    const int nodes = 1 << (L - h);
+    const int kmax = ceil_div(n, nodes) + 1;
+    const int n1max = ceil_div(kmax, 2) + 1;
+    const int nxt = 1 - cur;
+    const size_t smem = (size_t)kmax * 48;
+    const int use_smem = smem <= 200 * 1024 ? 1 : 0;
+    zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[nxt], bufld[nxt], bufs[nxt], n, map);
+    dc_prepare_kernel<<<dim3(nodes, batch), 256, use_smem ? smem : 0, st>>>(ws, e, dstride, h, lev, bufp[cur],
+                                                                            bufld[cur], bufs[cur], use_smem, map);
+    dc_secular_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, map);
+    dc_zhat_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, map);
+    dc_vectors_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, 0, st>>>(ws, h, map);
+    dc_gather_kernel<<<dim3(kmax, nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur],
+                                                              bufp[nxt], bufld[nxt], bufs[nxt], nodes, map);
+    count_launch(6);
+    GSCF_CHECK_LAUNCH();
+    GemmParams gp{};
+    gp.descs = ws.descs;
+    gp.kbatch = 1;
+    GSCF_TRY(launch_gemm(false, true, gp, nodes * batch * 2, n1max, kmax, st));
+    cur = nxt;
+    lev = 1 - lev;
+  }
+  // ---- final ascending order ----------------------------------------------------------------------------
+  dc_rank_kernel<<<dim3(std::max(1, ceil_div(n, 128)), batch), 128, 0, st>>>(ws, lev, info_dev, map);
+  dc_permute_kernel<<<dim3(n, batch), 128, 0, st>>>(ws, lev, bufp[cur], bufld[cur], bufs[cur], Z, ldz, strideZ, w,
+                                                    stride_w, info_dev, map);
+  count_launch(2);
+  GSCF_CHECK_LAUNCH();
+  return GSCF_B200_OK;
+}
+
+}  // namespace gscfb

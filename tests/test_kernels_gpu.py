@@ -217,3 +217,59 @@ def test_measure_peaks_runs(env):
     a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
     L.check(L.lib.gscf_b200_measure_peaks(C.byref(a), C.byref(b), C.byref(c)))
     assert a.value > 1.0 and b.value > 1.0 and c.value > 500.0
+
+
+def _syev_check(torch, L, method, mats, n, tolscale=1.0):
+    batch = len(mats)
+    ld = L.lib.gscf_b200_padded_ld(n)
+    buf = np.concatenate([colmajor(np.tril(a) + 3.0 * np.triu(np.ones_like(a), 1), ld) for a in mats])
+    dA = dev(torch, buf)
+    dw = torch.zeros(batch * n, dtype=torch.float64, device="cuda")
+    dZ = torch.zeros(batch * ld * n, dtype=torch.float64, device="cuda")
+    info = torch.full((batch,), 7, dtype=torch.int32, device="cuda")
+    wsz = L.lib.gscf_b200_syev_worksize(n, batch, method)
+    work = torch.zeros(max(1, wsz // 8 + 1), dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_syev(method, n, dA.data_ptr(), ld, ld * n, dw.data_ptr(), n, dZ.data_ptr(), ld, ld * n,
+                                 batch, work.data_ptr(), wsz, info.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert info.cpu().numpy().tolist() == [0] * batch
+    w = dw.cpu().numpy().reshape(batch, n)
+    Z = dZ.cpu().numpy().reshape(batch, n, ld)
+    for b, a in enumerate(mats):
+        wref = np.linalg.eigvalsh(a)
+        scale = max(1.0, np.abs(wref).max())
+        z = Z[b][:, :n].T
+        assert np.abs(w[b] - wref).max() < tolscale * 1e-13 * scale * n
+        assert np.abs(z.T @ z - np.eye(n)).max() < tolscale * 1e-13 * n
+        assert np.abs(a @ z - z * w[b]).max() < tolscale * 1e-13 * scale * n
+
+
+@pytest.mark.parametrize("n", [2, 5, 33, 64, 65, 130, 200, 257, 512, 1024])
+def test_syev_tridiag_dc(env, n):
+    torch, L = env
+    rng = np.random.default_rng(n + 5)
+    a = rng.standard_normal((n, n))
+    a = a + a.T
+    mats = [a]
+    if n <= 257:
+        # clustered spectrum (forces deflation through rotations) and a diagonal-ish matrix
+        q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        ev = np.repeat(np.arange(1, n // 3 + 2), 3)[:n].astype(float)
+        b = (q * ev) @ q.T
+        mats.append(0.5 * (b + b.T))
+        mats.append(np.diag(np.arange(n, dtype=float)) + 1e-9 * a)
+    _syev_check(torch, L, L.EIG_TRIDIAG_DC, mats, n)
+
+
+def test_syev_tridiag_dc_fock_like(env):
+    """The matrices the SCF feeds the solver: X^T F X of the synthetic problem, n = 384."""
+    torch, L = env
+    from oracle.synthetic import SyntheticDFProblem
+
+    p = SyntheticDFProblem(384, 48, n_aux=4, seed=2)
+    w, v = np.linalg.eigh(p.S)
+    X = (v / np.sqrt(w)) @ v.T
+    F, _, _ = p.fock(p.core_guess()[None])
+    A = X @ F[0] @ X
+    A = 0.5 * (A + A.T)
+    _syev_check(torch, L, L.EIG_TRIDIAG_DC, [A, X @ p.H @ X], 384)

@@ -191,7 +191,7 @@ def test_synthetic_parity_small(G, n, o, aux, which, kw):
         # well-conditioned and bound everything else by the loose convergence threshold
         lam = [float(c[0]) for c in got["trace"][2]]
         np.testing.assert_allclose(lam[:7], ref.trace_coeff[:7], rtol=1e-6, atol=1e-8)
-        np.testing.assert_allclose(lam, ref.trace_coeff, rtol=5e-3, atol=1e-8)
+        np.testing.assert_allclose(lam, ref.trace_coeff, rtol=5e-2, atol=1e-8)
         assert min(lam) < 0.9  # the damped branch really ran
         np.testing.assert_allclose(got["trace"][1], ref.trace_error, rtol=5e-2, atol=1e-12)
         assert np.abs(got["w"][0] - ref.orben[0]).max() < 1e-6
@@ -248,3 +248,17 @@ def test_ensemble_lockstep(G):
         n_checked += 1
     assert n_checked >= P // 2
     assert len(set(its.tolist())) > 1  # members really stop at different iterations
+
+
+@pytest.mark.parametrize("n,o,aux,m", [(160, 20, 8, 4), (256, 32, 16, 8)])
+def test_synthetic_parity_large_path(G, n, o, aux, m):
+    """DIIS through the tridiagonalisation + divide&conquer eigensolver (n > 128)."""
+    from gscf_b200 import lib as L
+
+    got = _run_synthetic(G, n, o, aux, "diis", params={"diis_n_prev_steps": m}, eig=L.EIG_TRIDIAG_DC)
+    ref, p = _oracle_synthetic(n, o, aux, "diis", n_prev_steps=m)
+    assert got["n_iter"] == ref.n_iter
+    assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
+    assert np.abs(got["w"][0] - ref.orben[0]).max() < TOL_EPS
+    assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < TOL_D
+    np.testing.assert_allclose(got["trace"][1], ref.trace_error, rtol=1e-5, atol=1e-12)
