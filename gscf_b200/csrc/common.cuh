@@ -37,6 +37,11 @@ const char* last_error_cstr();
 // Launch accounting for bench.py's gpu_launches claim.
 void count_launch(int n = 1);
 
+// Optional sub-phase timing (CUDA events on `st`); a no-op unless an engine enabled it.
+enum PhaseId { PH_TRIDIAG = 8, PH_STEDC = 9, PH_BACKTRANSFORM = 10, PH_SYMV_SAMPLE = 11, PH_ORTHO_GEMM = 12,
+               PH_TRAILING_GEMM = 13 };
+void phase_mark(int id, bool begin, cudaStream_t st);
+
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int ceil_div(int x, int m) { return (x + m - 1) / m; }
 inline long long ceil_div_ll(long long x, long long m) { return (x + m - 1) / m; }

@@ -75,7 +75,9 @@ struct gscf_b200_engine {
   // timings
   double scf_ms = 0.0, fock_ms = 0.0;
   bool phase_timing = false;
-  double phase_ms[8] = {0};
+  double phase_ms[16] = {0};
+  long long phase_count[16] = {0};
+  cudaEvent_t phase_open[16] = {nullptr};
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_spans;  // (phase, (a,b))

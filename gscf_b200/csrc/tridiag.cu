@@ -33,13 +33,16 @@ struct TrdWs {
   double* pdot;         // [cap][nrb]
   double* p12;          // [cap][nrb*2*NB]
   double* scal;         // [cap][8]   0: a[i+1]  1: raw w[i+1]
+  unsigned* bar;        // [cap] group barrier counters of the persistent panel kernel
+  int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
   double* Tf;           // [cap][NBQ*NBQ]
   double* Gm;           // [cap][NBQ*NBQ]
   double* Yw;           // [cap][NBQ*n]
   double* Y2;           // [cap][NBQ*n]
-  int n, ld, nrb, ncb;
+  int n, ld, nrb, ncb, cap;
 };
+inline int ws_cap_hint(const TrdWs& ws) { return ws.cap; }
 
 __device__ __forceinline__ void householder_scalars(double alpha, double xnorm2, double& beta, double& tau,
                                                      double& scale) {
@@ -66,7 +69,7 @@ trd_col_update(double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int i, 
   const int n = ws.n, li = i - j0;
   double* A = Ab + q * sA;
   double* W = ws.W + q * (long long)ws.ld * NB;
-  const double* pdot = ws.pdot + q * ws.nrb;
+  const double* pdot = ws.pdot + q * ws.npart;
   const double* tauv = ws.tau + q * n;
   double* scal = ws.scal + q * 8;
   if (threadIdx.x == 0) {
@@ -106,7 +109,7 @@ trd_col_update(double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int i, 
     if (r >= i + 2) part = a * a;
   }
   part = block_sum(part, red);
-  if (threadIdx.x == 0) (ws.pnorm + q * ws.nrb)[blockIdx.x] = part;
+  if (threadIdx.x == 0) (ws.pnorm + q * ws.npart)[blockIdx.x] = part;
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------
@@ -123,7 +126,7 @@ trd_symv(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int i, 
   const double* W = ws.W + q * (long long)ws.ld * NB;
   const double* scal = ws.scal + q * 8;
   if (threadIdx.x == 0) {
-    const double* pn = ws.pnorm + q * ws.nrb;
+    const double* pn = ws.pnorm + q * ws.npart;
     double x2 = 0.0;
     for (int b = 0; b < nrb_k1; ++b) x2 += pn[b];
     double beta, tau, scale;
@@ -199,7 +202,7 @@ trd_assemble_w(double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int i, 
   double* W = ws.W + q * (long long)ws.ld * NB;
   double* scal = ws.scal + q * 8;
   if (threadIdx.x == 0) {
-    const double* pn = ws.pnorm + q * ws.nrb;
+    const double* pn = ws.pnorm + q * ws.npart;
     double x2 = 0.0;
     for (int b = 0; b < nrb_k1; ++b) x2 += pn[b];
     double beta, tau, scale;
@@ -237,7 +240,7 @@ trd_assemble_w(double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int i, 
     part = w * v;
   }
   part = block_sum(part, red);
-  if (threadIdx.x == 0) (ws.pdot + q * ws.nrb)[blockIdx.x] = part;
+  if (threadIdx.x == 0) (ws.pdot + q * ws.npart)[blockIdx.x] = part;
 }
 
 // w_last += alpha v_last (rows >= i+1) at the end of a panel
@@ -250,7 +253,7 @@ trd_finalize_w(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, i
   const double* A = Ab + q * sA;
   double* W = ws.W + q * (long long)ws.ld * NB;
   if (threadIdx.x == 0) {
-    const double* pdot = ws.pdot + q * ws.nrb;
+    const double* pdot = ws.pdot + q * ws.npart;
     double s = 0.0;
     for (int b = 0; b < nrb_prev; ++b) s += pdot[b];
     s_alpha = -0.5 * (ws.tau + q * n)[i] * s;
@@ -314,6 +317,12 @@ __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __re
   (void)ws; (void)dout; (void)eout; (void)map;
 }
 
+}  // namespace
+}  // namespace gscfb
+#include "trd_panel.cuh"
+namespace gscfb {
+namespace {
+
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Carver {
@@ -329,16 +338,18 @@ struct Carver {
 
 void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   const int ld = padded_ld(n);
-  ws.n = n; ws.ld = ld;
+  ws.n = n; ws.ld = ld; ws.cap = cap;
   ws.nrb = ceil_div(n, RB);
-  ws.ncb = ceil_div(n, TS);
+  ws.ncb = ceil_div(n, 32);
+  ws.npart = std::max(ws.nrb, 1024);
   ws.d = cv.take<double>((size_t)cap * n);
   ws.e = cv.take<double>((size_t)cap * n);
   ws.tau = cv.take<double>((size_t)cap * n);
   ws.W = cv.take<double>((size_t)cap * ld * NB);
   ws.ypart = cv.take<double>((size_t)cap * ws.ncb * n);
-  ws.pnorm = cv.take<double>((size_t)cap * ws.nrb);
-  ws.pdot = cv.take<double>((size_t)cap * ws.nrb);
+  ws.pnorm = cv.take<double>((size_t)cap * ws.npart);
+  ws.pdot = cv.take<double>((size_t)cap * ws.npart);
+  ws.bar = cv.take<unsigned>((size_t)cap);
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
@@ -348,8 +359,8 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.Y2 = cv.take<double>((size_t)cap * NBQ * n);
 }
 
-int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
-                   cudaStream_t st) {
+int tridiagonalise_legacy(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
+                          cudaStream_t st) {
   int nrb_prev_dot = 0;  // row blocks that wrote pdot in the previous K3
   if (n == 1) {
     trd_col_update<<<dim3(1, batch), RB, 0, st>>>(A, lda, sA, ws, 0, 0, 0, map);
@@ -364,7 +375,10 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
       trd_col_update<<<dim3(nrb1, batch), RB, 0, st>>>(A, lda, sA, ws, i, j0, nrb_prev_dot, map);
       const int m = n - i - 1;  // trailing order
       const int ntr = ceil_div(m, TS), ntc = ceil_div(m, TS);
+      const bool sample = (i % 8) == 4;  // bench.py roofline: every 8th symv launch is event-timed
+      if (sample) phase_mark(PH_SYMV_SAMPLE, true, st);
       trd_symv<<<dim3(ntr * ntc + ntr, batch), TS, 0, st>>>(A, lda, sA, ws, i, j0, nrb1, ntr, ntc, map);
+      if (sample) phase_mark(PH_SYMV_SAMPLE, false, st);
       const int nrb3 = ceil_div(m, RB);
       trd_assemble_w<<<dim3(nrb3, batch), RB, 0, st>>>(A, lda, sA, ws, i, j0, nrb1, ntr, ntc, map);
       count_launch(3);
@@ -381,6 +395,7 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
       count_launch();
       // trailing update A22 -= V2 W2^T + W2 V2^T on rows/cols >= j0 + pw
       const int r0 = j0 + pw, mt = n - r0;
+      phase_mark(PH_TRAILING_GEMM, true, st);
       GemmParams g = gemm_params(mt, mt, pw, -1.0, A + (size_t)j0 * lda + r0, lda, ws.W + r0, ws.ld, 1.0,
                                  A + (size_t)r0 * lda + r0, lda);
       g.sA = sA; g.sB = (long long)ws.ld * NB; g.sC = sA; g.batch_map = map;
@@ -389,9 +404,78 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
                                  A + (size_t)r0 * lda + r0, lda);
       h.sA = (long long)ws.ld * NB; h.sB = sA; h.sC = sA; h.batch_map = map;
       GSCF_TRY(launch_gemm(false, true, h, batch, mt, mt, st));
+      phase_mark(PH_TRAILING_GEMM, false, st);
       nrb_prev_dot = 0;
     }
     GSCF_CHECK_LAUNCH();
+  }
+  return GSCF_B200_OK;
+}
+
+
+// Persistent-panel driver: one cooperative launch per panel + the deferred rank-2k GEMM update.
+int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
+                   cudaStream_t st) {
+  static int legacy = -1, g_override = 0, capacity = 0;
+  if (legacy < 0) {
+    const char* env = getenv("GSCF_B200_TRD_LEGACY");
+    legacy = (env && env[0] == '1') ? 1 : 0;
+    const char* ge = getenv("GSCF_B200_TRD_G");
+    g_override = ge ? atoi(ge) : 0;
+    int dev = 0, sms = 0, per_sm = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel, PT, 0);
+    capacity = sms * per_sm;
+    if (!coop || capacity < 1) legacy = 1;
+  }
+  if (legacy || n < 3) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
+  const int gmin = ceil_div(n, PT);
+  if (gmin > capacity) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
+  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, (size_t)ws_cap_hint(ws) * sizeof(unsigned), st));
+  int sms = capacity;  // upper bound for one matrix: one CTA per SM is the sweet spot for the barrier
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  unsigned bar_base = 0;
+  for (int j0 = 0; j0 < n - 1; j0 += NB) {
+    const int pw = std::min(NB, n - 1 - j0);
+    const int last_panel = (j0 + pw == n - 1) ? 1 : 0;
+    const int m = n - j0 - 1;
+    const int tiles = ceil_div(m, SR) * ceil_div(m, SC) + ceil_div(m, SR);
+    int G = g_override > 0 ? g_override : std::min(tiles, std::max(1, sms / std::max(1, std::min(batch, sms))));
+    G = std::max(G, gmin);
+    G = std::min(G, std::min(capacity, GMAX));
+    const int per_launch = std::max(1, capacity / G);
+    for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
+      const int cnt = std::min(per_launch, batch - mat0);
+      double* Aarg = A; int ldaarg = lda; long long sAarg = sA; TrdWs wsarg = ws;
+      int j0arg = j0, pwarg = pw, lastarg = last_panel, mat0arg = mat0;
+      unsigned basearg = bar_base;
+      const int* maparg = map;
+      void* args[] = {&Aarg, &ldaarg, &sAarg, &wsarg, &j0arg, &pwarg, &lastarg, &basearg, &maparg, &mat0arg};
+      phase_mark(PH_SYMV_SAMPLE, true, st);  // id 11 = the persistent panel kernel (bench.py roofline)
+      GSCF_CUDA_TRY(cudaLaunchCooperativeKernel((void*)trd_panel_kernel, dim3(G, cnt), dim3(PT), args, 0, st));
+      phase_mark(PH_SYMV_SAMPLE, false, st);
+      count_launch();
+    }
+    bar_base += 3u * (unsigned)pw * (unsigned)G;
+    if (!last_panel) {
+      const int r0 = j0 + pw, mt = n - r0;
+      phase_mark(PH_TRAILING_GEMM, true, st);
+      GemmParams g = gemm_params(mt, mt, pw, -1.0, A + (size_t)j0 * lda + r0, lda, ws.W + r0, ws.ld, 1.0,
+                                 A + (size_t)r0 * lda + r0, lda);
+      g.sA = sA; g.sB = (long long)ws.ld * NB; g.sC = sA; g.batch_map = map;
+      GSCF_TRY(launch_gemm(false, true, g, batch, mt, mt, st));
+      GemmParams h = gemm_params(mt, mt, pw, -1.0, ws.W + r0, ws.ld, A + (size_t)j0 * lda + r0, lda, 1.0,
+                                 A + (size_t)r0 * lda + r0, lda);
+      h.sA = (long long)ws.ld * NB; h.sB = sA; h.sC = sA; h.batch_map = map;
+      GSCF_TRY(launch_gemm(false, true, h, batch, mt, mt, st));
+      phase_mark(PH_TRAILING_GEMM, false, st);
+    }
   }
   return GSCF_B200_OK;
 }
@@ -468,9 +552,15 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   carve_trd(cv, n, cap, ws);
   StedcWs dws;
   stedc_carve((char*)work, cv.off, n, cap, dws);
+  phase_mark(PH_TRIDIAG, true, st);
   GSCF_TRY(tridiagonalise(n, A, lda, strideA, ws, batch, batch_map, st));
+  phase_mark(PH_TRIDIAG, false, st);
+  phase_mark(PH_STEDC, true, st);
   GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st));
+  phase_mark(PH_STEDC, false, st);
+  phase_mark(PH_BACKTRANSFORM, true, st);
   GSCF_TRY(back_transform(n, A, lda, strideA, ws, Z, ldz, strideZ, batch, batch_map, st));
+  phase_mark(PH_BACKTRANSFORM, false, st);
   return GSCF_B200_OK;
 }
 

@@ -410,10 +410,14 @@ class Engine:
         return a.value, b.value
 
     def phase_timings(self):
-        out = np.zeros(8)
-        L.check(L.lib.gscf_b200_get_phase_timings(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), 8))
-        return dict(diagmat=out[0], eig=out[1], density=out[2], error=out[3], coeff=out[4], fock=out[5],
-                    total=out[6])
+        out = np.zeros(32)
+        L.check(L.lib.gscf_b200_get_phase_timings(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), 32))
+        names = {0: "diagmat", 1: "eig", 2: "density", 3: "error", 4: "coeff", 5: "fock", 6: "total",
+                 8: "tridiag", 9: "stedc", 10: "backtransform", 11: "panel_kernel", 12: "ortho_gemm",
+                 13: "trailing_gemm"}
+        res = {v: float(out[k]) for k, v in names.items()}
+        res["counts"] = {v: int(out[16 + k]) for k, v in names.items()}
+        return res
 
     # used by ScfState while hooks run
     def refresh_eigensolution(self, state):
