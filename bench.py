@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py - SCF-iteration throughput of the gscf hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (libgscf_b200.so on the GPU)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the CPU restatement of the
+                                                           reference algorithm (oracle/, LAPACK) on the
+                                                           host cores - the reference itself cannot be
+                                                           built here (un-vendored lazyten/krims).
+
+A *step* is one complete SCF solve of one batch of synthetic input: core guess, then PulayDiisScf
+to convergence.  Default workload (N = 1): BASELINE configs[1] - synthetic closed-shell DF problem
+n_bf = 1024, n_occ = 128, DIIS depth 8, fp64.  With N > 1 every rank solves an independent replica
+(a single large problem stays on one GPU, north_star); the only collective is the NCCL gather of
+per-problem energies / iteration counts / convergence flags.
+
+metric  scf_iterations_per_s = SCF iterations / time in the SCF path, Fock builder excluded
+        (SURVEY 8d).  `value` uses CUDA-event device time (orthogonaliser set-up + solve loop);
+        `e2e` is the same metric with HOST input buffers: wall clock around
+        set_overlap(host S) + guess(host H) + solve + read-back of C, eps, energies, minus the
+        event-timed Fock-builder time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_bf, n_alpha, n_beta, n_aux, diis depth, problems per GPU)
+    "c2": dict(n=1024, na=128, nb=128, aux=64, m=8, P=1, desc="configs[1]: n_bf=1024 n_occ=128 DIIS 8"),
+    "c3": dict(n=4096, na=512, nb=512, aux=64, m=10, P=1, desc="configs[2]: n_bf=4096 n_occ=512 DIIS 10 (n_aux=64)"),
+    "c4": dict(n=128, na=16, nb=16, aux=8, m=4, P=4096, desc="configs[3]: 4096 x n_bf=128 ensemble, DIIS 4"),
+    "c5": dict(n=512, na=64, nb=60, aux=32, m=4, P=256, desc="configs[4]: 256 x UHF n_bf=512 ensemble, DIIS 4"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: oracle timed on the host cores (cpu_baseline leg and --impl reference)
+# ---------------------------------------------------------------------------------------------
+def oracle_time_solve(w, seed, max_iter=None):
+    """One DIIS solve of the oracle; returns (n_iter, scf_path_seconds, fock_seconds, energy)."""
+    from oracle import ScfFailed, pulay_diis_scf
+    from oracle.synthetic import SyntheticDFProblem
+
+    prob = SyntheticDFProblem(w["n"], w["na"], w["nb"], n_aux=w["aux"], seed=seed)
+    fock_t = [0.0]
+    inner = prob.fock
+
+    def timed_fock(C):
+        t0 = time.perf_counter()
+        out = inner(C)
+        fock_t[0] += time.perf_counter() - t0
+        return out
+
+    prob.fock = timed_fock
+    C0 = prob.core_guess()
+    C0 = np.stack([C0, C0]) if prob.unrestricted else C0[None]
+    F0, e1, e2 = inner(C0)
+    fock_t[0] = 0.0
+    t0 = time.perf_counter()
+    n_iter, energy = 0, float("nan")
+    try:
+        res = pulay_diis_scf(prob, F0, e1, e2, n_prev_steps=w["m"], max_iter=max_iter or 100)
+        n_iter, energy = res.n_iter, res.energy_total
+    except ScfFailed:
+        n_iter = max_iter or 100  # bounded sample: the iterations were executed and timed
+    total = time.perf_counter() - t0
+    return n_iter, total - fock_t[0], fock_t[0], energy
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    sample_iters = 3 if w["n"] >= 1024 else 6
+    sample = f"{sample_iters} DIIS iterations of one {w['desc']} problem per step (BLAS threads = all cores)"
+    times, iters = [], []
+    for s in range(args.warmup + args.steps):
+        n_it, t_scf, t_fock, _ = oracle_time_solve(w, seed=0, max_iter=sample_iters)
+        if s >= args.warmup:
+            times.append(t_scf)
+            iters.append(n_it)
+    value = sum(iters) / sum(times)
+    line = {
+        "impl": "reference", "metric": "scf_iterations_per_s", "value": value, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "impl": "oracle/ (numpy + scipy LAPACK dsygvd/dgesv/dgemm): the reference's "
+                   "lazyten/armadillo path cannot be built (un-vendored dependencies)", "fock_builder": "excluded"},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+
+    import gscf_b200 as G
+    from gscf_b200 import lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (gscf_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, na, nb, aux, m = w["n"], w["na"], w["nb"], w["aux"], w["m"]
+    ensemble = w["P"] > 1
+    # ensembles are sharded (strong scaling of the fixed ensemble); single problems are replicated
+    P_total = args.problems or w["P"]
+    if ensemble:
+        P_local = P_total // world
+        seeds = list(range(rank * P_local, (rank + 1) * P_local))
+    else:
+        P_local = 1
+        seeds = [rank]
+    unrestricted = na != nb
+    nblk = 2 if unrestricted else 1
+
+    fock = G.DeviceDFFock(n, na, nb, n_aux=aux, seeds=seeds)
+    ld = fock.ld
+    # HOST copies of the inputs of the path (S and the core Hamiltonian), pinned
+    S_host = torch.empty((P_local, n, n), dtype=torch.float64).pin_memory()
+    H_host = torch.empty((P_local, n, n), dtype=torch.float64).pin_memory()
+    for p in range(P_local):
+        L.check(L.lib.gscf_b200_copy_matrix(S_host[p].data_ptr(), n, L.HOST, fock.overlap_ptr() + p * ld * n * 8, ld,
+                                            L.DEVICE, n, n))
+        L.check(L.lib.gscf_b200_copy_matrix(H_host[p].data_ptr(), n, L.HOST, fock.core_ptr() + p * ld * n * 8, ld,
+                                            L.DEVICE, n, n))
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+
+    params = L.Params()
+    L.lib.gscf_b200_default_params(__import__("ctypes").byref(params))
+    params.diis_n_prev_steps = m
+    fn_ptr, ctx = fock.device_callback()
+
+    eng = G.Engine(n, na, nb, n_blocks=nblk, n_problems=P_local, max_history=max(m, 2))
+    eng.set_fock_device(fn_ptr, ctx)
+    eng.set_phase_timing(True)
+
+    def one_step():
+        """One solve through the public API with HOST inputs; returns per-step measurements."""
+        flush.zero_()  # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.check(L.lib.gscf_b200_set_overlap(eng.handle, S_host.data_ptr(), n, L.HOST))
+        L.check(L.lib.gscf_b200_set_guess_from_matrix(eng.handle, H_host.data_ptr(), n, L.HOST))
+        st = eng.solve("diis", params)
+        its = eng.n_iter()
+        e1, e2 = eng.energies()
+        w_ = eng.orben()
+        Cm = eng.get_matrix("coeff")
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        scf_ms, fock_ms = eng.timings()
+        ph = eng.phase_timings()
+        return dict(status=st, iters=its.copy(), e=(e1 + e2).copy(), conv=eng.converged().copy(), wall=wall,
+                    scf_ms=scf_ms, fock_ms=fock_ms, overlap_ms=ph["overlap"], ph=ph,
+                    d2h=w_.nbytes + Cm.nbytes + e1.nbytes + e2.nbytes)
+
+    for _ in range(args.warmup):
+        one_step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.lib.gscf_b200_launch_count()
+    t_begin = time.perf_counter()
+    steps = [one_step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t_total = time.perf_counter() - t_begin
+    launches = L.lib.gscf_b200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    iters_local = float(sum(int(s["iters"].sum()) for s in steps))
+    conv_local = float(sum(int(s["conv"].sum()) for s in steps))
+    dev_s = sum(s["scf_ms"] + s["overlap_ms"] for s in steps) / 1e3       # device time in the SCF path
+    e2e_s = sum(s["wall"] - s["fock_ms"] / 1e3 for s in steps)            # host-buffer wall time, Fock excluded
+    fock_s = sum(s["fock_ms"] for s in steps) / 1e3
+    red = torch.tensor([dev_s, e2e_s, t_total, fock_s], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([iters_local, conv_local, float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)  # device times: max over ranks
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        # the path's only collective: gather per-problem energies / iteration counts / flags
+        last = steps[-1]
+        rec = torch.tensor(np.stack([last["e"], last["iters"].astype(float), last["conv"].astype(float)], 1),
+                           dtype=torch.float64, device="cuda")
+        gathered = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(gathered, rec)
+        ensemble_table = torch.cat(gathered).cpu().numpy()
+    else:
+        last = steps[-1]
+        ensemble_table = np.stack([last["e"], last["iters"].astype(float), last["conv"].astype(float)], 1)
+    dev_s, e2e_s, t_total, fock_s = [float(x) for x in red.cpu()]
+    iters_all, conv_all, launches_all = [float(x) for x in tot.cpu()]
+
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        ph = steps[-1]["ph"]
+        # dominant kernel: the persistent panel kernel of the tridiagonalisation (large path) or
+        # the shared-memory Jacobi kernel (ensembles of small problems)
+        roofline = None
+        n_eig = int(steps[-1]["iters"].max())
+        if ph["counts"].get("panel_kernel", 0) > 0:
+            launches_k = ph["counts"]["panel_kernel"]
+            avg_s = ph["panel_kernel"] / 1e3 / launches_k
+            # algorithmic bytes: one triangle of the trailing matrix per column, 4 (n-i-1)^2 bytes
+            total_bytes = sum(4.0 * (n - i - 1) ** 2 for i in range(n - 1)) * nblk * P_local
+            per_launch = total_bytes * n_eig / launches_k  # n_eig tridiagonalisations in the solve loop
+            ach = per_launch / avg_s / 1e9
+            roofline = {"kernel": "trd_panel_kernel (Householder panel: symv + reflector algebra)", "bound": "hbm",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                        "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches_per_solve": launches_k,
+                        "share_of_scf_path": ph["panel_kernel"] / max(1e-9, steps[-1]["scf_ms"])}
+        flops_it = 7.0 * n ** 3 + 10.0 * n * n * na
+        fp64_tf = flops_it * (iters_all / args.steps / world) * nblk / (dev_s / args.steps) / 1e12 if dev_s > 0 else 0.0
+        line = {
+            "metric": "scf_iterations_per_s", "value": iters_all / dev_s, "unit": "iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "strong" if ensemble else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "problems_per_gpu": P_local, "n_bf": n, "n_alpha": na, "n_beta": nb,
+                       "n_aux": aux, "diis_depth": m, "iterations_per_solve": int(steps[-1]["iters"].max()),
+                       "parallelism": ("ensemble sharded by problem index" if ensemble else
+                                       "independent replica per GPU (single problem stays on one GPU)"),
+                       "timing": "value: CUDA-event device time of orthogonaliser set-up + solve loop, Fock builder "
+                                 "excluded; e2e: wall clock with host S/H in, C/eps/E out, Fock builder excluded",
+                       "l2": "256 MiB buffer written between steps (L2 flush)",
+                       "scf_ms_per_step": 1e3 * dev_s / args.steps, "fock_ms_per_step": 1e3 * fock_s / args.steps,
+                       "phase_ms_last_step": {k: v for k, v in ph.items() if k != "counts"},
+                       "fp64_useful_tflops": fp64_tf, "problems_converged_per_s": conv_all / dev_s,
+                       "energies_last_step": [float(x) for x in ensemble_table[:4, 0]]},
+            "clocks": clocks,
+            "e2e": {"value": iters_all / e2e_s, "unit": "iterations/s",
+                    "h2d_bytes_per_step": int(2 * P_local * n * n * 8), "d2h_bytes_per_step": int(steps[-1]["d2h"])},
+            "gpu_launches": int(launches_all),
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_it, t_scf, t_fock, e_ref = oracle_time_solve(w if not ensemble else dict(w), seed=seeds[0])
+            line["cpu_baseline"] = {"value": n_it / t_scf, "unit": "iterations/s", "cores": os.cpu_count(),
+                                    "kind": "port",
+                                    "sample": f"1 full DIIS solve ({n_it} iterations) of problem seed {seeds[0]} on the host "
+                                              f"(oracle/: LAPACK dsygvd + dgemm, all BLAS threads); Fock builder excluded",
+                                    "energy_abs_diff_vs_gpu": abs(e_ref - float(steps[-1]["e"][0]))}
+        print(json.dumps(line))
+    eng.close()
+    fock.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--problems", type=int, default=0, help="ensemble size override (c4/c5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

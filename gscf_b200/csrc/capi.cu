@@ -166,6 +166,19 @@ int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds
   return GSCF_B200_OK;
 }
 
+int gscf_b200_copy_matrix(void* dst, int ld_dst, int dst_loc, const void* src, int ld_src, int src_loc, int rows,
+                          int cols) {
+  GSCF_TRY(have_device());
+  cudaMemcpyKind kind = cudaMemcpyDefault;
+  if (dst_loc == GSCF_B200_HOST && src_loc == GSCF_B200_DEVICE) kind = cudaMemcpyDeviceToHost;
+  else if (dst_loc == GSCF_B200_DEVICE && src_loc == GSCF_B200_HOST) kind = cudaMemcpyHostToDevice;
+  else if (dst_loc == GSCF_B200_DEVICE && src_loc == GSCF_B200_DEVICE) kind = cudaMemcpyDeviceToDevice;
+  else kind = cudaMemcpyHostToHost;
+  GSCF_CUDA_TRY(cudaMemcpy2D(dst, (size_t)ld_dst * sizeof(double), src, (size_t)ld_src * sizeof(double),
+                             (size_t)rows * sizeof(double), cols, kind));
+  return GSCF_B200_OK;
+}
+
 double gscf_b200_compute_damping_coeff(double oda_s, double oda_c, double min_fock_prefactor) {
   return compute_damping_coeff(oda_s, oda_c, min_fock_prefactor);
 }

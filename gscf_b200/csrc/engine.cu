@@ -61,6 +61,7 @@ void collect_timings(Engine* e) {
   e->ev_used = 0;
   e->fock_ms = e->phase_ms[PH_FOCK];
   e->scf_ms = e->phase_ms[PH_TOTAL] - e->fock_ms;
+  e->phase_ms[7] = e->overlap_ms;
 }
 
 thread_local Engine* g_cur_engine = nullptr;
@@ -596,6 +597,10 @@ int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int meml
   if (!e || !S || ld < e->n) return GSCF_B200_ERR_INVALID_ARG;
   const int n = e->n;
   const int cnt_in = e->cfg.shared_overlap ? 1 : e->P;
+  cudaEvent_t ov_a = nullptr, ov_b = nullptr;
+  cudaEventCreate(&ov_a);
+  cudaEventCreate(&ov_b);
+  cudaEventRecord(ov_a, e->stream);
   // per-problem overlaps are duplicated per block so that every matrix-level GEMM sees one stride
   if (e->cfg.shared_overlap) {
     GSCF_TRY(copy_in(e, e->S, e->mstride, S, ld, memloc, 1));
@@ -619,7 +624,15 @@ int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int meml
   std::vector<double> wh((size_t)nm * n);
   GSCF_CUDA_TRY(cudaMemcpyAsync(info.data(), e->eiginfo, nm * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   GSCF_CUDA_TRY(cudaMemcpyAsync(wh.data(), wtmp, wh.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  cudaEventRecord(ov_b, e->stream);
   GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ov_a, ov_b);
+    e->overlap_ms = ms;  // orthogonaliser set-up (H2D of S + S^-1/2), reported as phase 7
+    cudaEventDestroy(ov_a);
+    cudaEventDestroy(ov_b);
+  }
   for (int i = 0; i < nm; ++i) {
     if (info[i] != 0) { set_last_error("eigensolver failed on the overlap matrix"); return GSCF_B200_ERR_EIGENSOLVER; }
     if (!(wh[(size_t)i * n] > 0.0)) { set_last_error("overlap matrix is not positive definite"); return GSCF_B200_ERR_INVALID_ARG; }

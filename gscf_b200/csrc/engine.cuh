@@ -73,7 +73,7 @@ struct gscf_b200_engine {
   gscf_b200_hook_fn hook = nullptr;
   void* hook_ctx = nullptr;
   // timings
-  double scf_ms = 0.0, fock_ms = 0.0;
+  double scf_ms = 0.0, fock_ms = 0.0, overlap_ms = 0.0;
   bool phase_timing = false;
   double phase_ms[16] = {0};
   long long phase_count[16] = {0};

@@ -80,6 +80,7 @@ SIGNATURES = {
     "gscf_b200_pulay_error_worksize": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gscf_b200_pulay_error": (C.c_int, [C.c_int, C.c_int, C.c_double, _P, C.c_int, _LL, _P, C.c_int, _LL,
                                         _P, C.c_int, _LL, _P, C.c_int, _LL, _P, _LL, C.c_int, _P]),
+    "gscf_b200_copy_matrix": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gscf_b200_compute_damping_coeff": (C.c_double, [C.c_double, C.c_double, C.c_double]),
     "gscf_b200_default_params": (None, [C.POINTER(Params)]),
     "gscf_b200_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),

@@ -122,6 +122,10 @@ int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds
                           void* stream);
 size_t gscf_b200_pulay_error_worksize(int n, int n_occ, int batch);
 
+/* Copy a rows x cols fp64 column-major matrix between host / device buffers (memloc flags). */
+int gscf_b200_copy_matrix(void* dst, int ld_dst, int dst_loc, const void* src, int ld_src, int src_loc,
+                          int rows, int cols);
+
 /* compute_damping_coeff of TruncatedOptDampScf.hh:370-394 (host, exact control flow). */
 double gscf_b200_compute_damping_coeff(double oda_s, double oda_c, double min_fock_prefactor);
 
