@@ -1079,6 +1079,15 @@ int gscf_b200_get_diis_coefficients(gscf_b200_engine* e, double* c, int* n_coeff
   }
   return GSCF_B200_OK;
 }
+int gscf_b200_get_current_diis_coefficients(gscf_b200_engine* e, double* c, int k) {
+  if (!e || !c || k < 0 || k > kMaxHistory) return GSCF_B200_ERR_INVALID_ARG;
+  std::vector<double> h((size_t)e->P * kMaxHistory);
+  GSCF_CUDA_TRY(cudaMemcpyAsync(h.data(), e->coeff, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (int p = 0; p < e->P; ++p)
+    for (int j = 0; j < k; ++j) c[(size_t)p * k + j] = h[(size_t)p * kMaxHistory + j];
+  return GSCF_B200_OK;
+}
 int gscf_b200_get_error_overlaps(gscf_b200_engine* e, int problem, int entry, double* ov, int* len) {
   if (!e || !ov || !len || problem < 0 || problem >= e->P) return GSCF_B200_ERR_INVALID_ARG;
   const int k = (int)e->hist_order.size();

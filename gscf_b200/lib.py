@@ -111,6 +111,7 @@ SIGNATURES = {
     "gscf_b200_get_density": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_error": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_diis_coefficients": (C.c_int, [_P, _D, _I]),
+    "gscf_b200_get_current_diis_coefficients": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_error_overlaps": (C.c_int, [_P, C.c_int, C.c_int, _D, _I]),
     "gscf_b200_get_damping_coeff": (C.c_int, [_P, _D]),
     "gscf_b200_get_trace": (C.c_int, [_P, C.c_int, _D, _D, _D, C.c_int, _I]),

@@ -1,0 +1,3 @@
+// gscf-b200: same header name as src/gscf/version.hh of the reference; everything lives in gscf.hh
+#pragma once
+#include "gscf.hh"

@@ -257,6 +257,9 @@ int gscf_b200_get_error(gscf_b200_engine* e, double* E, int ld);
 /* DIIS state mirrors (PulayDiisScfState :56-86): coefficients oldest->newest of the last
  * extrapolation, [P][max_history], count returned through n_coeff. */
 int gscf_b200_get_diis_coefficients(gscf_b200_engine* e, double* c, int* n_coeff);
+/* Coefficients of the extrapolation being diagonalised right now (valid inside the NEW_DIAGMAT /
+ * UPDATE_EIGENPAIRS hooks), [P][k] oldest -> newest. */
+int gscf_b200_get_current_diis_coefficients(gscf_b200_engine* e, double* c, int k);
 /* overlap vector of ring entry i (oldest = 0), newest-first like PulayDiisScf.hh:67-70 */
 int gscf_b200_get_error_overlaps(gscf_b200_engine* e, int problem, int entry, double* ov, int* len);
 int gscf_b200_get_damping_coeff(gscf_b200_engine* e, double* damp);    /* TODA, [P] */
