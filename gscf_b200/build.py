@@ -43,7 +43,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         path = os.path.join(CSRC, src)
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("GSCF_B200_EXTRA_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

@@ -110,6 +110,95 @@ GSCF_HD inline double secular_root(int K, int i, const double* d, const double* 
   return dorg + tau;
 }
 
+#if defined(__CUDACC__)
+// Warp-parallel variant of secular_root: the 32 lanes split the K poles of every function evaluation
+// (butterfly sums, so all lanes hold identical scalars and take identical branches).  Same iteration,
+// same stopping rule.  All lanes of the warp must call it; the result is valid in every lane.
+__device__ inline double secular_root_warp(int K, int i, const double* __restrict__ d, const double* __restrict__ z,
+                                           double rho, double* __restrict__ delta, long long dstride) {
+  const int lane = threadIdx.x & 31;
+  auto wsum = [](double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  if (K == 1) {
+    const double tau = rho * z[0] * z[0];
+    if (lane == 0) delta[0] = -tau;
+    return d[0] + tau;
+  }
+  const bool last = (i == K - 1);
+  int io;
+  double lo, hi, tau;
+  if (!last) {
+    const double di = d[i];
+    const double del = d[i + 1] - di;
+    const double mid = 0.5 * del;
+    double g = 0.0;
+    for (int j = lane; j < K; j += 32) g += rho * z[j] * z[j] / ((d[j] - di) - mid);
+    g = 1.0 + wsum(g);
+    if (g >= 0.0) { io = i; lo = 0.0; hi = mid; tau = mid; }
+    else { io = i + 1; lo = -mid; hi = 0.0; tau = -mid; }
+  } else {
+    double zz = 0.0;
+    for (int j = lane; j < K; j += 32) zz += z[j] * z[j];
+    zz = wsum(zz);
+    io = K - 1; lo = 0.0; hi = rho * zz; tau = 0.5 * hi;
+    hi = hi * (1.0 + 8.0 * kDcEps) + 1e-300;
+  }
+  const double dorg = d[io];
+  const int isplit = last ? K - 1 : i;
+  const double dsp = d[isplit] - dorg;
+  const double dsp1 = last ? 0.0 : d[isplit + 1] - dorg;
+  for (int it = 0; it < 100; ++it) {
+    double psi = 0.0, dpsi = 0.0, phi = 0.0, dphi = 0.0;
+    for (int j = lane; j < K; j += 32) {
+      const double x = (d[j] - dorg) - tau;
+      const double t = z[j] / x;
+      const double a = rho * z[j] * t, b = rho * t * t;
+      if (j <= isplit) { psi += a; dpsi += b; } else { phi += a; dphi += b; }
+    }
+    psi = wsum(psi); dpsi = wsum(dpsi); phi = wsum(phi); dphi = wsum(dphi);
+    const double g = 1.0 + psi + phi;
+    const double erretm = 8.0 * (phi - psi) + 2.0 + fabs(tau) * (dpsi + dphi);
+    if (fabs(g) <= kDcEps * erretm) break;
+    if (g < 0.0) { if (tau > lo) lo = tau; } else { if (tau < hi) hi = tau; }
+    double t_new;
+    const double D1 = dsp - tau;
+    if (!last) {
+      const double D2 = dsp1 - tau;
+      const double a = dpsi * D1 * D1, A = dphi * D2 * D2;
+      const double c = 1.0 + (psi - dpsi * D1) + (phi - dphi * D2);
+      const double qa = c, qb = c * (D1 + D2) + a + A, qc = D1 * D2 * g;
+      double eta;
+      if (qa == 0.0) {
+        eta = qc / qb;
+      } else {
+        double disc = qb * qb - 4.0 * qa * qc;
+        if (disc < 0.0) disc = 0.0;
+        const double qq = 0.5 * (qb + copysign(sqrt(disc), qb));
+        const double e2 = qc / qq, e1 = qq / qa;
+        const double t2 = tau + e2, t1 = tau + e1;
+        if (t2 > lo && t2 < hi) eta = e2;
+        else if (t1 > lo && t1 < hi) eta = e1;
+        else eta = NAN;
+      }
+      t_new = tau + eta;
+    } else {
+      const double a = dpsi * D1 * D1;
+      const double c = 1.0 + (psi - dpsi * D1);
+      t_new = (c > 0.0) ? tau + (D1 + a / c) : NAN;
+    }
+    if (!(t_new > lo && t_new < hi)) t_new = 0.5 * (lo + hi);
+    if (t_new == tau || !(hi - lo > 0.0)) break;
+    if (hi - lo <= 2.0 * kDcEps * fmax(fabs(lo), fabs(hi))) { tau = t_new; break; }
+    tau = t_new;
+  }
+  for (int j = lane; j < K; j += 32) delta[(long long)j * dstride] = (d[j] - dorg) - tau;
+  return dorg + tau;
+}
+#endif
+
 // Deflation of one merge (the logic of LAPACK dlaed2 restated).  d, z: combined eigenvalues and
 // (normalised) z vector of the two children, k entries; idx: permutation sorting d ascending;
 // ctype[j] in {1 (column lives in the top rows), 3 (bottom rows)} on input, may become 2 (mixed).

@@ -21,7 +21,7 @@ namespace gscfb {
 
 namespace {
 
-constexpr int kLeaf = 64;  // maximum leaf order
+constexpr int kLeaf = 32;  // maximum leaf order
 
 __host__ __device__ inline int bnd(int i, int n, int L) { return (int)(((long long)i * n) >> L); }
 
@@ -221,7 +221,7 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
 }
 
 // ---- merge: secular equation --------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 dc_secular_kernel(StedcWs ws, int h, int lev_out, const int* __restrict__ map) {
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
@@ -229,12 +229,12 @@ dc_secular_kernel(StedcWs ws, int h, int lev_out, const int* __restrict__ map) {
   const NodeGeom g = node_geom(t, h, n, ws.L);
   const int lo = g.lo;
   const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per root
   if (i >= K) return;
   const double rho = (ws.rho + (size_t)q * ws.nleaf)[t];
   double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;  // node block, [j*ld + i]
-  const double lam = secular_root(K, i, ws.dlamda + q * n + lo, ws.w + q * n + lo, rho, S + i, ws.ld, nullptr);
-  (ws.lam[lev_out] + q * n + lo)[i] = lam;
+  const double lam = secular_root_warp(K, i, ws.dlamda + q * n + lo, ws.w + q * n + lo, rho, S + i, ws.ld);
+  if ((threadIdx.x & 31) == 0) (ws.lam[lev_out] + q * n + lo)[i] = lam;
 }
 
 // zhat_j = sign(w_j) sqrt( - delta(j,j) * prod_{i != j} delta(j,i) / (d_j - d_i) )
@@ -262,28 +262,37 @@ dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   if (lane == 0) (ws.zhat + q * n + lo)[j] = copysign(sqrt(fabs(p)), (ws.w + q * n + lo)[j]);
 }
 
-// U^T[gpos[j]][i] = zhat_j / delta(j,i) / ||.||   (thread per eigenvector i)
-__global__ void __launch_bounds__(128)
+// U^T[gpos[j]][i] = zhat_j / delta(j,i) / ||.||.  CTA = 32 eigenvectors (lane) x 8 warps splitting the poles.
+__global__ void __launch_bounds__(256)
 dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
+  __shared__ double snrm[8][33];
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
   const int n = ws.n;
   const NodeGeom g = node_geom(t, h, n, ws.L);
   const int lo = g.lo;
   const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= K) return;
+  if (blockIdx.x * 32 >= K) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
   const double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
   double* U = ws.U + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
   const double* zh = ws.zhat + q * n + lo;
   const int* gpos = ws.gpos + q * n + lo;
   double nrm = 0.0;
-  for (int j = 0; j < K; ++j) {
-    const double u = zh[j] / S[(size_t)j * ws.ld + i];
-    nrm = fma(u, u, nrm);
-  }
-  const double inv = 1.0 / sqrt(nrm);
-  for (int j = 0; j < K; ++j) U[(size_t)gpos[j] * ws.ld + i] = zh[j] / S[(size_t)j * ws.ld + i] * inv;
+  if (i < K)
+    for (int j = warp; j < K; j += 8) {
+      const double u = zh[j] / S[(size_t)j * ws.ld + i];
+      nrm = fma(u, u, nrm);
+    }
+  snrm[warp][lane] = nrm;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += snrm[w][lane];
+  const double inv = 1.0 / sqrt(tot);
+  if (i < K)
+    for (int j = warp; j < K; j += 8) U[(size_t)gpos[j] * ws.ld + i] = zh[j] / S[(size_t)j * ws.ld + i] * inv;
 }
 
 // Gather non-deflated columns (grouped by type) into Gq, copy deflated columns/eigenvalues to the
@@ -448,9 +457,9 @@ int stedc_batched(int n, const double* d, const double* e, long long dstride, do
     zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[nxt], bufld[nxt], bufs[nxt], n, map);
     dc_prepare_kernel<<<dim3(nodes, batch), 256, use_smem ? smem : 0, st>>>(ws, e, dstride, h, lev, bufp[cur],
                                                                             bufld[cur], bufs[cur], use_smem, map);
-    dc_secular_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, map);
+    dc_secular_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, 1 - lev, map);
     dc_zhat_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, map);
-    dc_vectors_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, 0, st>>>(ws, h, map);
+    dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, map);
     dc_gather_kernel<<<dim3(kmax, nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur],
                                                               bufp[nxt], bufld[nxt], bufs[nxt], nodes, map);
     count_launch(6);

@@ -34,6 +34,7 @@ struct TrdWs {
   double* p12;          // [cap][nrb*2*NB]
   double* scal;         // [cap][8]   0: a[i+1]  1: raw w[i+1]
   unsigned* bar;        // [cap] group barrier counters of the persistent panel kernel
+  double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
   int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
   double* Tf;           // [cap][NBQ*NBQ]
@@ -313,6 +314,45 @@ __global__ void larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ m
   for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) Tg[idx] = T[idx];
 }
 
+// Y2 = T Y without forming T: T^-1 = diag(1/tau) + striu(V^T V) (upper triangular), so the rows of
+// Y2 follow by back substitution  Y2[j] = tau_j (Y[j] - sum_{k>j} G(j,k) Y2[k]),  j = pw-1 .. 0.
+// One thread per right-hand side (a column of Z); G and tau in shared memory.  tau_j = 0 (H_j = I)
+// gives Y2[j] = 0, consistent with T(j,:) = T(:,j) = 0.
+template <int PW>
+__global__ void __launch_bounds__(128)
+wy_trsm_kernel(TrdWs ws, int j0, int pw, int ncols, const int* __restrict__ map) {
+  __shared__ double sG[PW * PW];
+  __shared__ double stau[PW];
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const double* Gg = ws.Gm + q * NBQ * NBQ;  // ld = pw
+  const double* tau = ws.tau + q * ws.n + j0;
+  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) sG[idx] = Gg[idx];
+  for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = tau[idx];
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const double* y = ws.Yw + q * (long long)NBQ * ws.n + (size_t)c * NBQ;
+  double* y2 = ws.Y2 + q * (long long)NBQ * ws.n + (size_t)c * NBQ;
+  double x[PW];
+#pragma unroll
+  for (int j = 0; j < PW; ++j) x[j] = j < pw ? y[j] : 0.0;
+#pragma unroll
+  for (int j = PW - 1; j >= 0; --j) {
+    if (j < pw) {
+      double s0 = x[j], s1 = 0.0;
+#pragma unroll
+      for (int k = j + 1; k < PW; k += 2) {
+        if (k < pw) s0 = fma(-sG[k * pw + j], x[k], s0);         // G(j,k) = G[k*pw + j] (column-major)
+        if (k + 1 < pw && k + 1 < PW) s1 = fma(-sG[(k + 1) * pw + j], x[k + 1], s1);
+      }
+      x[j] = stau[j] * (s0 + s1);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PW; ++j)
+    if (j < pw) y2[j] = x[j];
+}
+
 __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __restrict__ eout, const int* map) {
   (void)ws; (void)dout; (void)eout; (void)map;
 }
@@ -320,6 +360,7 @@ __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __re
 }  // namespace
 }  // namespace gscfb
 #include "trd_panel.cuh"
+#include "trd_cluster.cuh"
 namespace gscfb {
 namespace {
 
@@ -350,6 +391,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.pnorm = cv.take<double>((size_t)cap * ws.npart);
   ws.pdot = cv.take<double>((size_t)cap * ws.npart);
   ws.bar = cv.take<unsigned>((size_t)cap);
+  ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
@@ -413,6 +455,44 @@ int tridiagonalise_legacy(int n, double* A, int lda, long long sA, const TrdWs& 
 }
 
 
+__global__ void pack_vw_kernel(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int j0, int pw, int r0,
+                               const int* __restrict__ map) {
+  // VW = [V2 | W2], WV = [W2 | V2]  (rows r0.., pw columns each) so that the rank-2k update is ONE GEMM
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const double* A = Ab + q * sA;
+  const double* W = ws.W + q * (long long)ws.ld * NB;
+  double* VW = ws.VW + q * (long long)ws.ld * 4 * NB;
+  double* WV = VW + (long long)ws.ld * 2 * NB;
+  const int m = ws.n - r0;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < m * pw; idx += gridDim.x * blockDim.x) {
+    const int j = idx / m, rr = idx - j * m;
+    const double v = A[(size_t)(j0 + j) * lda + r0 + rr];
+    const double w = W[(size_t)j * ws.ld + r0 + rr];
+    VW[(size_t)j * ws.ld + rr] = v;
+    VW[(size_t)(pw + j) * ws.ld + rr] = w;
+    WV[(size_t)j * ws.ld + rr] = w;
+    WV[(size_t)(pw + j) * ws.ld + rr] = v;
+  }
+}
+
+// A22 -= V2 W2^T + W2 V2^T = [V2 | W2] [W2 | V2]^T on rows / columns >= j0 + pw (one pass over A22)
+int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, int j0, int pw, int batch,
+                    const int* map, cudaStream_t st) {
+  const int r0 = j0 + pw, mt = n - r0;
+  if (mt <= 0) return GSCF_B200_OK;
+  phase_mark(PH_TRAILING_GEMM, true, st);
+  pack_vw_kernel<<<dim3(std::max(1, std::min(64, ceil_div(mt * pw, 256))), batch), 256, 0, st>>>(A, lda, sA, ws, j0, pw,
+                                                                                             r0, map);
+  count_launch();
+  GSCF_CHECK_LAUNCH();
+  GemmParams g = gemm_params(mt, mt, 2 * pw, -1.0, ws.VW, ws.ld, ws.VW + (size_t)ws.ld * 2 * NB, ws.ld, 1.0,
+                             A + (size_t)r0 * lda + r0, lda);
+  g.sA = g.sB = (long long)ws.ld * 4 * NB; g.sC = sA; g.batch_map = map;
+  GSCF_TRY(launch_gemm(false, true, g, batch, mt, mt, st));
+  phase_mark(PH_TRAILING_GEMM, false, st);
+  return GSCF_B200_OK;
+}
+
 // Persistent-panel driver: one cooperative launch per panel + the deferred rank-2k GEMM update.
 int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                    cudaStream_t st) {
@@ -431,6 +511,59 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
     if (!coop || capacity < 1) legacy = 1;
   }
   if (legacy || n < 3) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
+  // ---- thread-block-cluster path for L2-resident matrices ------------------------------------------
+  static int cluster_mode = -1;  // 1: available, 0: unavailable / disabled
+  if (cluster_mode < 0) {
+    const char* env = getenv("GSCF_B200_TRD_CLUSTER");
+    cluster_mode = (env && env[0] == '0') ? 0 : 1;
+    if (cluster_mode) {
+      if (cudaFuncSetAttribute(trd_cluster_panel_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+          cudaFuncSetAttribute(trd_cluster_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+                cudaSuccess) {
+        cudaGetLastError();
+        cluster_mode = 0;
+      }
+    }
+  }
+  if (cluster_mode && n <= CL_MAXN) {
+    int C = batch < 4 ? 16 : 8;
+    const char* ce = getenv("GSCF_B200_TRD_CLUSTER_SIZE");
+    if (ce) C = atoi(ce);
+    while (C > 1 && (n + C - 1) / C < 8) C /= 2;  // tiny matrices: fewer CTAs
+    const size_t smem = trd_cluster_smem_bytes(n, C);
+    if ((n + C - 1) / C <= CT && smem <= 200 * 1024) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(C, 1);
+      cfg.blockDim = dim3(CT);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int max_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, trd_cluster_panel_kernel, &cfg) == cudaSuccess && max_clusters > 0) {
+        for (int j0 = 0; j0 < n - 1; j0 += NB) {
+          const int pw = std::min(NB, n - 1 - j0);
+          const int last_panel = (j0 + pw == n - 1) ? 1 : 0;
+          for (int mat0 = 0; mat0 < batch; mat0 += 32768) {
+            const int cnt = std::min(32768, batch - mat0);
+            cfg.gridDim = dim3(C, cnt);
+            phase_mark(PH_SYMV_SAMPLE, true, st);
+            GSCF_CUDA_TRY(cudaLaunchKernelEx(&cfg, trd_cluster_panel_kernel, A, lda, sA, ws, j0, pw, last_panel,
+                                             map ? map + mat0 : (const int*)nullptr));
+            phase_mark(PH_SYMV_SAMPLE, false, st);
+            count_launch();
+            if (!map && mat0 > 0) return GSCF_B200_ERR_NOT_IMPLEMENTED;  // > 32768 unmapped matrices: not needed
+          }
+          if (!last_panel) GSCF_TRY(trailing_update(n, A, lda, sA, ws, j0, pw, batch, map, st));
+        }
+        return GSCF_B200_OK;
+      }
+      cudaGetLastError();
+    }
+  }
   const int gmin = ceil_div(n, PT);
   if (gmin > capacity) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
   GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, (size_t)ws_cap_hint(ws) * sizeof(unsigned), st));
@@ -446,7 +579,10 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
     const int last_panel = (j0 + pw == n - 1) ? 1 : 0;
     const int m = n - j0 - 1;
     const int tiles = ceil_div(m, SR) * ceil_div(m, SC) + ceil_div(m, SR);
-    int G = g_override > 0 ? g_override : std::min(tiles, std::max(1, sms / std::max(1, std::min(batch, sms))));
+    // single large matrices are bandwidth-bound: 2 CTAs per SM keep enough loads in flight (measured at n = 4096:
+    // 297 / 220 / 189 ms for 0.5 / 1 / 2 CTAs per SM)
+    const int per_mat = batch == 1 ? 2 * sms : std::max(1, sms / std::max(1, std::min(batch, sms)));
+    int G = g_override > 0 ? g_override : std::min(tiles, per_mat);
     G = std::max(G, gmin);
     G = std::min(G, std::min(capacity, GMAX));
     const int per_launch = std::max(1, capacity / G);
@@ -463,19 +599,7 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
       count_launch();
     }
     bar_base += 3u * (unsigned)pw * (unsigned)G;
-    if (!last_panel) {
-      const int r0 = j0 + pw, mt = n - r0;
-      phase_mark(PH_TRAILING_GEMM, true, st);
-      GemmParams g = gemm_params(mt, mt, pw, -1.0, A + (size_t)j0 * lda + r0, lda, ws.W + r0, ws.ld, 1.0,
-                                 A + (size_t)r0 * lda + r0, lda);
-      g.sA = sA; g.sB = (long long)ws.ld * NB; g.sC = sA; g.batch_map = map;
-      GSCF_TRY(launch_gemm(false, true, g, batch, mt, mt, st));
-      GemmParams h = gemm_params(mt, mt, pw, -1.0, ws.W + r0, ws.ld, A + (size_t)j0 * lda + r0, lda, 1.0,
-                                 A + (size_t)r0 * lda + r0, lda);
-      h.sA = (long long)ws.ld * NB; h.sB = sA; h.sC = sA; h.batch_map = map;
-      GSCF_TRY(launch_gemm(false, true, h, batch, mt, mt, st));
-      phase_mark(PH_TRAILING_GEMM, false, st);
-    }
+    if (!last_panel) GSCF_TRY(trailing_update(n, A, lda, sA, ws, j0, pw, batch, map, st));
   }
   return GSCF_B200_OK;
 }
@@ -498,17 +622,14 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     GemmParams g = gemm_params(pw, pw, m, 1.0, ws.Vc, ws.ld, ws.Vc, ws.ld, 0.0, ws.Gm, pw);
     g.sA = g.sB = (long long)ws.ld * NBQ; g.sC = NBQ * NBQ; g.batch_map = map;
     GSCF_TRY(launch_gemm(true, false, g, batch, pw, pw, st));
-    larft_kernel<<<batch, 64, 2 * pw * pw * sizeof(double), st>>>(ws, j0, pw, map);
-    count_launch();
-    GSCF_CHECK_LAUNCH();
     // Y = Vc^T Z(j0+1:, :)   (pw x n, ld NBQ)
     GemmParams y = gemm_params(pw, n, m, 1.0, ws.Vc, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
     y.sA = (long long)ws.ld * NBQ; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
     GSCF_TRY(launch_gemm(true, false, y, batch, pw, n, st));
-    // Y2 = T Y
-    GemmParams t = gemm_params(pw, n, pw, 1.0, ws.Tf, pw, ws.Yw, NBQ, 0.0, ws.Y2, NBQ);
-    t.sA = NBQ * NBQ; t.sB = t.sC = (long long)NBQ * n; t.batch_map = map;
-    GSCF_TRY(launch_gemm(false, false, t, batch, pw, n, st));
+    // Y2 = T Y by back substitution with T^-1 = diag(1/tau) + striu(G)
+    wy_trsm_kernel<NBQ><<<dim3(ceil_div(n, 128), batch), 128, 0, st>>>(ws, j0, pw, n, map);
+    count_launch();
+    GSCF_CHECK_LAUNCH();
     // Z(j0+1:, :) -= Vc Y2
     GemmParams u = gemm_params(m, n, pw, -1.0, ws.Vc, ws.ld, ws.Y2, NBQ, 1.0, Z + j0 + 1, ldz);
     u.sA = (long long)ws.ld * NBQ; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;
