@@ -9,6 +9,7 @@
 //     !TB: sB[n][k]  ld = BK+4      TB: sB[k][n]  ld = BN+4
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 namespace gscfb {
@@ -72,7 +73,8 @@ dgemm_dmma_kernel(const GemmParams p) {
     A = d.A; B = d.B; C = d.C; m = d.m; n = d.n; k = d.k;
     lda = d.lda; ldb = d.ldb; ldc = d.ldc; alpha = d.alpha; beta = d.beta;
   } else {
-    const long long z = p.batch_map ? p.batch_map[blockIdx.z] : blockIdx.z;
+    const int ze = p.ksplit > 1 ? blockIdx.z / p.ksplit : blockIdx.z;
+    const long long z = p.batch_map ? p.batch_map[ze] : ze;
     A = p.A + z * p.sA; B = p.B + z * p.sB; C = p.C + z * p.sC;
     m = p.m; n = p.n; k = p.k; lda = p.lda; ldb = p.ldb; ldc = p.ldc;
     alpha = p.alpha; beta = p.beta;
@@ -91,7 +93,14 @@ dgemm_dmma_kernel(const GemmParams p) {
 
   const int kbatch = p.descs ? 1 : p.kbatch;
   const int ktiles_per = (k + BK - 1) / BK;
-  const int KT = ktiles_per * kbatch;
+  int KT = ktiles_per * kbatch;
+  int T0 = 0;  // first k-tile of this CTA (split-k)
+  if (p.ksplit > 1) {
+    const int split = blockIdx.z % p.ksplit;
+    const int per = (KT + p.ksplit - 1) / p.ksplit;
+    T0 = split * per;
+    KT = min(KT, T0 + per);
+  }
 
   auto load_tile = [&](int stage, int t) {
     const int q = t / ktiles_per;
@@ -124,16 +133,17 @@ dgemm_dmma_kernel(const GemmParams p) {
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < KT) load_tile(s, s);
+    if (T0 + s < KT) load_tile(s, T0 + s);
     cp_async_commit();
   }
 
-  for (int t = 0; t < KT; ++t) {
+  for (int tt = 0; tt < KT - T0; ++tt) {
+    const int t = tt;
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     {
       const int tn = t + STAGES - 1;
-      if (tn < KT) load_tile(tn % STAGES, tn);
+      if (T0 + tn < KT) load_tile(tn % STAGES, T0 + tn);
       cp_async_commit();
     }
     const double* sA = smem + (t % STAGES) * L::STAGE_ELEMS;
@@ -160,6 +170,21 @@ dgemm_dmma_kernel(const GemmParams p) {
   cp_async_wait<0>();
 
   // ---- epilogue ----------------------------------------------------------------------------
+  if (p.ksplit > 1) {  // split-k: raw partial tile, reduced (alpha, beta applied) by splitk_reduce_kernel
+    double* Cp = p.Cpart + (size_t)blockIdx.z * m * n;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int r = m0 + wm + i * 8 + lr;
+      if (r >= m) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int c = n0 + wn + j * 8 + 2 * lc;
+        if (c < n) Cp[(size_t)c * m + r] = acc[i][j][0];
+        if (c + 1 < n) Cp[(size_t)(c + 1) * m + r] = acc[i][j][1];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
     const int r = m0 + wm + i * 8 + lr;
@@ -206,6 +231,38 @@ static int launch_t(const GemmParams& p, int batch, int max_m, int max_n, cudaSt
   if (big_tiles >= 120)
     return launch_cfg<128, 128, 16, 64, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
   return launch_cfg<64, 64, 16, 32, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
+}
+
+__global__ void splitk_reduce_kernel(GemmParams p, int splits) {
+  const int ze = blockIdx.y;
+  const long long z = p.batch_map ? p.batch_map[ze] : ze;
+  double* C = p.C + z * p.sC;
+  const double* part = p.Cpart + (size_t)ze * splits * p.m * p.n;
+  const int total = p.m * p.n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < splits; ++k) s += part[(size_t)k * total + idx];
+    const int c = idx / p.m, r = idx - c * p.m;
+    double* dst = C + (size_t)c * p.ldc + r;
+    double v = p.alpha * s;
+    if (p.beta != 0.0) v += p.beta * (*dst);
+    *dst = v;
+  }
+}
+
+int launch_gemm_splitk(bool ta, bool tb, GemmParams p, int batch, int splits, double* work, cudaStream_t st) {
+  if (splits <= 1 || work == nullptr) {
+    p.ksplit = 1;
+    return launch_gemm(ta, tb, p, batch, p.m, p.n, st);
+  }
+  p.ksplit = splits;
+  p.Cpart = work;
+  GSCF_TRY(launch_gemm(ta, tb, p, batch * splits, p.m, p.n, st));
+  const int total = p.m * p.n;
+  splitk_reduce_kernel<<<dim3(std::max(1, std::min(64, ceil_div(total, 256))), batch), 256, 0, st>>>(p, splits);
+  count_launch();
+  GSCF_CHECK_LAUNCH();
+  return GSCF_B200_OK;
 }
 
 int launch_gemm(bool ta, bool tb, const GemmParams& p, int batch, int max_m, int max_n,

@@ -32,6 +32,8 @@ struct GemmParams {
   double alpha, beta;
   const int* batch_map;   // optional: batch entry z works on problem batch_map[z]
   const GemmDesc* descs;  // optional: grouped mode, one descriptor per blockIdx.z
+  int ksplit;             // > 1: split-k, blockIdx.z = entry * ksplit + split, partial tiles go to Cpart
+  double* Cpart;          // [batch * ksplit][m * n] partial products (compact, ld = m)
 };
 
 inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A, int lda,
@@ -41,6 +43,7 @@ inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A
   p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
   p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
+  p.ksplit = 1; p.Cpart = nullptr;
   return p;
 }
 
@@ -55,6 +58,10 @@ inline int gemm(bool ta, bool tb, int m, int n, int k, double alpha, const doubl
   GemmParams p = gemm_params(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   return launch_gemm(ta, tb, p, 1, m, n, st);
 }
+// Split-k variant for small outputs with a long k (TN products of the back-transformation): `splits`
+// CTAs share one output tile, partials are reduced by a second kernel.  work: batch*splits*m*n doubles.
+int launch_gemm_splitk(bool ta, bool tb, GemmParams p, int batch, int splits, double* work, cudaStream_t stream);
+
 inline int gemm_batched(bool ta, bool tb, int m, int n, int k, double alpha, const double* A,
                         int lda, long long sA, const double* B, int ldb, long long sB,
                         double beta, double* C, int ldc, long long sC, int batch,

@@ -35,6 +35,7 @@ struct TrdWs {
   double* scal;         // [cap][8]   0: a[i+1]  1: raw w[i+1]
   unsigned* bar;        // [cap] group barrier counters of the persistent panel kernel
   double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
+  double* SK;           // split-k partials: min(cap,16) * 16 * NBQ * n
   int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
   double* Tf;           // [cap][NBQ*NBQ]
@@ -321,36 +322,42 @@ __global__ void larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ m
 template <int PW>
 __global__ void __launch_bounds__(128)
 wy_trsm_kernel(TrdWs ws, int j0, int pw, int ncols, const int* __restrict__ map) {
-  __shared__ double sG[PW * PW];
+  // G^T in shared memory (row j of G contiguous), the solution vectors of the CTA's 128 right-hand
+  // sides in shared memory as x[j][thread]: runtime loops (a fully unrolled register version was
+  // instruction-cache bound: 91 us per launch)
+  extern __shared__ double sm_trsm[];
+  double* sGt = sm_trsm;                   // [PW][PW+1]: sGt[j*(PW+1) + k] = G(j,k)
+  double* sx = sGt + PW * (PW + 1);        // [PW][128]
   __shared__ double stau[PW];
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
-  const double* Gg = ws.Gm + q * NBQ * NBQ;  // ld = pw
+  const double* Gg = ws.Gm + q * NBQ * NBQ;  // column-major, ld = pw
   const double* tau = ws.tau + q * ws.n + j0;
-  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) sG[idx] = Gg[idx];
-  for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = tau[idx];
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  const double* y = ws.Yw + q * (long long)NBQ * ws.n + (size_t)c * NBQ;
-  double* y2 = ws.Y2 + q * (long long)NBQ * ws.n + (size_t)c * NBQ;
-  double x[PW];
-#pragma unroll
-  for (int j = 0; j < PW; ++j) x[j] = j < pw ? y[j] : 0.0;
-#pragma unroll
-  for (int j = PW - 1; j >= 0; --j) {
-    if (j < pw) {
-      double s0 = x[j], s1 = 0.0;
-#pragma unroll
-      for (int k = j + 1; k < PW; k += 2) {
-        if (k < pw) s0 = fma(-sG[k * pw + j], x[k], s0);         // G(j,k) = G[k*pw + j] (column-major)
-        if (k + 1 < pw && k + 1 < PW) s1 = fma(-sG[(k + 1) * pw + j], x[k + 1], s1);
-      }
-      x[j] = stau[j] * (s0 + s1);
-    }
+  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
+    const int k = idx / pw, jj = idx - k * pw;  // G(jj, k)
+    sGt[jj * (PW + 1) + k] = Gg[idx];
   }
-#pragma unroll
-  for (int j = 0; j < PW; ++j)
-    if (j < pw) y2[j] = x[j];
+  for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = tau[idx];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = c < ncols;
+  const double* y = ws.Yw + q * (long long)NBQ * ws.n + (size_t)(act ? c : 0) * NBQ;
+  double* y2 = ws.Y2 + q * (long long)NBQ * ws.n + (size_t)(act ? c : 0) * NBQ;
+  for (int jj = 0; jj < pw; ++jj) sx[jj * 128 + threadIdx.x] = act ? y[jj] : 0.0;
+  __syncthreads();
+  for (int jj = pw - 1; jj >= 0; --jj) {
+    const double* grow = sGt + jj * (PW + 1);
+    double s0 = sx[jj * 128 + threadIdx.x], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = jj + 1;
+    for (; k + 4 <= pw; k += 4) {
+      s0 = fma(-grow[k], sx[k * 128 + threadIdx.x], s0);
+      s1 = fma(-grow[k + 1], sx[(k + 1) * 128 + threadIdx.x], s1);
+      s2 = fma(-grow[k + 2], sx[(k + 2) * 128 + threadIdx.x], s2);
+      s3 = fma(-grow[k + 3], sx[(k + 3) * 128 + threadIdx.x], s3);
+    }
+    for (; k < pw; ++k) s0 = fma(-grow[k], sx[k * 128 + threadIdx.x], s0);
+    sx[jj * 128 + threadIdx.x] = stau[jj] * ((s0 + s1) + (s2 + s3));
+  }
+  if (act)
+    for (int jj = 0; jj < pw; ++jj) y2[jj] = sx[jj * 128 + threadIdx.x];
 }
 
 __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __restrict__ eout, const int* map) {
@@ -392,6 +399,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.pdot = cv.take<double>((size_t)cap * ws.npart);
   ws.bar = cv.take<unsigned>((size_t)cap);
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
+  ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
@@ -621,13 +629,15 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     // G = Vc^T Vc  (pw x pw, ld pw)
     GemmParams g = gemm_params(pw, pw, m, 1.0, ws.Vc, ws.ld, ws.Vc, ws.ld, 0.0, ws.Gm, pw);
     g.sA = g.sB = (long long)ws.ld * NBQ; g.sC = NBQ * NBQ; g.batch_map = map;
-    GSCF_TRY(launch_gemm(true, false, g, batch, pw, pw, st));
+    const int splits = batch >= 16 ? 1 : std::max(1, std::min(16, m / 128));  // long-k TN products: split-k
+    GSCF_TRY(launch_gemm_splitk(true, false, g, batch, splits, ws.SK, st));
     // Y = Vc^T Z(j0+1:, :)   (pw x n, ld NBQ)
     GemmParams y = gemm_params(pw, n, m, 1.0, ws.Vc, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
     y.sA = (long long)ws.ld * NBQ; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
-    GSCF_TRY(launch_gemm(true, false, y, batch, pw, n, st));
+    GSCF_TRY(launch_gemm_splitk(true, false, y, batch, std::min(splits, 8), ws.SK, st));
     // Y2 = T Y by back substitution with T^-1 = diag(1/tau) + striu(G)
-    wy_trsm_kernel<NBQ><<<dim3(ceil_div(n, 128), batch), 128, 0, st>>>(ws, j0, pw, n, map);
+    wy_trsm_kernel<NBQ><<<dim3(ceil_div(n, 128), batch), 128, (NBQ * (NBQ + 1) + NBQ * 128) * sizeof(double), st>>>(
+        ws, j0, pw, n, map);
     count_launch();
     GSCF_CHECK_LAUNCH();
     // Z(j0+1:, :) -= Vc Y2
@@ -662,6 +672,8 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   if (!cfg) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        2 * NBQ * NBQ * (int)sizeof(double)));
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(wy_trsm_kernel<NBQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (NBQ * (NBQ + 1) + NBQ * 128) * (int)sizeof(double)));
     cfg = true;
   }
   // capacity: derive from the workspace size so that batch_map indices stay in range
