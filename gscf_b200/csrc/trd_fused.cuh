@@ -1,0 +1,304 @@
+// Fused Householder tridiagonalisation (included by tridiag.cu): ONE launch for the whole reduction,
+// ONE cross-CTA exchange per column.
+//
+// A group of G CTAs owns one matrix, columns dealt out cyclically (column c -> CTA c mod G).  The
+// owned columns live in shared memory when they fit (n = 1024 on 148 CTAs: 56 KiB each; n = 512 on
+// a 16-CTA cluster: 128 KiB each), otherwise they are updated in place in global memory (L2).
+//
+// The classical unblocked step (LAPACK dsytd2) for column j is
+//     y = A22 v_j,  w_j = tau_j (y - 1/2 tau_j (y^T v_j) v_j),  A22 -= v_j w_j^T + w_j v_j^T,
+// followed by the Householder vector v_{j+1} of the updated column j+1.  Its global dependencies
+// are (a) every entry of y, (b) the updated column j+1.  With full symmetric storage and column
+// ownership y_c = A22(:,c)^T v_j is local to the owner of column c, so the only exchange is an
+// all-gather of y (n - j - 1 numbers) plus the raw column j+1 from its owner.  Everything that
+// follows (y^T v, w_j, the updated column, its norm, v_{j+1}, tau_{j+1}) is O(n) work and is
+// recomputed redundantly - and bit-identically - by every CTA, so no second exchange is needed.
+// The rank-2 update with (v_j, w_j) is then fused with the product for the NEXT column:
+//     pass j+1:  for my columns c >= j+2:  A(:,c) -= v_j w_j(c) + w_j v_j(c);  y'_c = A(:,c)^T v_{j+1}
+// i.e. one read+write sweep over the CTA's part of the trailing matrix per column, no deferred
+// panel update, no V/W correction terms, no trailing GEMM.
+//
+// The exchange goes through L2: producers store y_c / the raw column into a double-buffered slot, one
+// thread per CTA fences and bumps a monotonic arrival counter and spins on it, then every thread loads
+// the slot once.  (Measured on B200, scripts/micro/exchange.cu: polling the data itself - "data as
+// flag" - costs ~10k cycles per step with 148 CTAs hammering the same lines; the counter scheme ~3.5k.)
+// The CTAs of a group must be co-resident: thread-block cluster launch (G <= 16, batches) or
+// cooperative launch (G up to the SM count, single large matrices).  The wait is bounded (clock64
+// timeout + global abort flag); an aborted reduction poisons d[0] with NaN so that the divide &
+// conquer stage flags the matrix as failed.
+#pragma once
+
+namespace gscfb {
+namespace {
+
+constexpr int TF_MAXS = 48;  // owned columns per CTA (n <= 48 G)
+constexpr int TF_CG = 8;     // columns per register group in the sweep (independent 16-byte loads in flight)
+
+struct TfArgs {
+  double* A; int lda; long long sA;
+  double* X;             // [cap][2][2 np] exchange slots (parity of the step): y at [c], raw column j+1 at [np + r]
+  unsigned* ctr;         // [cap] arrival counters, zero on entry
+  double *d, *e, *tau;   // [cap][n]
+  unsigned* abort_flag;  // one word, zero on entry
+  const int* map; int mat0; int n;
+};
+
+__device__ __forceinline__ double tf_ld(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tf_st(double* p, double v) {
+  asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void tf_st2(double* p, double x, double y) {
+  asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
+}
+// offset of entry r inside a step's chunked exchange slot (see the kernel)
+__device__ __forceinline__ unsigned tf_ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool tf_is_sentinel(double v) { return __double_as_longlong(v) == -1LL; }
+
+// sum over the block, valid in every thread; one __syncthreads (the caller alternates `red` buffers)
+template <int T>
+__device__ __forceinline__ double tf_block_sum(double v, double* red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) s += red[w];
+  return s;
+}
+
+inline long long tf_x_doubles(int n) { return 4LL * ((n + 1) & ~1); }
+inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
+  const int np = round_up(n, 2);
+  const int S = ceil_div(n, G);
+  return ((size_t)3 * np + 32 * TF_MAXS + 32 + 32 + 8 + (smem_a ? (size_t)S * np : 0)) * sizeof(double);
+}
+
+template <int KMAX, bool SMEM_A, int T>
+__global__ void __launch_bounds__(T, 1)
+trd_fused_kernel(const TfArgs a) {
+  const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = T / 32;
+  const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
+  const int n = a.n, lda = a.lda, np = (n + 1) & ~1;
+  double* __restrict__ A = a.A + q * a.sA;
+  double* X = a.X + q * 4LL * np;
+  unsigned* ctr = a.ctr + q;
+
+  extern __shared__ __align__(16) double tf_smem[];
+  double* sv0 = tf_smem;
+  double* sv1 = sv0 + np;
+  double* sw = sv1 + np;
+  double* spart = sw + np;             // [32][TF_MAXS] per-warp partial y
+  double* sred1 = spart + 32 * TF_MAXS;
+  double* sred2 = sred1 + 32;
+  double* sbc = sred2 + 32;            // 0: y[first]  1: a'[first+1]
+  double* sAc = sbc + 8;               // SMEM_A: owned columns, slot s at sAc + s*np
+
+  const int S = g < n ? (n - g + G - 1) / G : 0;  // owned columns c = g + s G
+
+  for (int r = tid; r < np; r += T) { sv0[r] = 0.0; sv1[r] = 0.0; sw[r] = 0.0; }
+  if (tid < 8) sbc[tid] = 0.0;
+  if (SMEM_A) {
+    for (int s = 0; s < S; ++s) {
+      const double* src = A + (size_t)(g + s * G) * lda;
+      for (int r = tid; r < np; r += T) sAc[(size_t)s * np + r] = r < n ? src[r] : 0.0;
+    }
+  }
+  __syncthreads();
+
+  double* svc = sv0;  // v_j      (zero above row j+1, one at row j+1)
+  double* svn = sv1;  // v_{j+1}
+  double tau_j = 0.0;
+
+#ifdef GSCF_TF_DEBUG_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tmark = clock64();
+#define TF_TICK(k) do { const long long _t = clock64(); tacc[k] += _t - tmark; tmark = _t; } while (0)
+#else
+#define TF_TICK(k) do { } while (0)
+#endif
+  for (int j = -1; j <= n - 2; ++j) {
+    const int first = j + 1;
+    double yv[KMAX], rv[KMAX];
+    TF_TICK(7);
+    if (j < 0) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int r = tid + k * T;
+        yv[k] = 0.0;
+        rv[k] = r < n ? A[r] : 0.0;  // column 0 as it came in
+      }
+    } else {
+      // ================= sweep: apply reflector j-1 to my columns, multiply them with v_j ==================
+      const int s0 = first > g ? (first - g + G - 1) / G : 0;
+      const int r_lo = first & ~1;
+      const int npairs = (np - r_lo) >> 1;
+      double* Xy = X + (size_t)(j & 1) * 2 * np;
+      double* Xr = Xy + np;
+      const bool pub_raw = (g + s0 * G == first);  // I own column j+1: its updated values are the raw column
+      for (int sg = s0; sg < S; sg += TF_CG) {
+        double acc[TF_CG], wc[TF_CG], vc[TF_CG];
+#pragma unroll
+        for (int u = 0; u < TF_CG; ++u) {
+          const int slot = sg + u;
+          const int c = g + slot * G;
+          acc[u] = 0.0;
+          wc[u] = slot < S ? sw[c] : 0.0;   // w_{j-1}(c)
+          vc[u] = slot < S ? svn[c] : 0.0;  // v_{j-1}(c): after the swap svn holds the previous reflector
+        }
+        for (int p = tid; p < npairs; p += T) {
+          const int r = r_lo + 2 * p;
+          const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
+          const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
+          const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
+          double2 av[TF_CG];
+#pragma unroll
+          for (int u = 0; u < TF_CG; ++u) {
+            const int slot = sg + u;
+            if (slot < S) {
+              const double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+              av[u] = *reinterpret_cast<const double2*>(col + r);
+            }
+          }
+          const bool odd_tail = !SMEM_A && (r + 1 >= n);  // pad row of an odd-order matrix in global memory
+#pragma unroll
+          for (int u = 0; u < TF_CG; ++u) {
+            const int slot = sg + u;
+            if (slot < S) {
+              double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+              double2 x = av[u];
+              x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+              x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+              if (odd_tail) {
+                x.y = 0.0;
+                col[r] = x.x;
+              } else {
+                *reinterpret_cast<double2*>(col + r) = x;
+              }
+              if (pub_raw && slot == s0) *reinterpret_cast<double2*>(Xr + r) = x;
+              acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < TF_CG; ++u) {
+          const double s = warp_sum(acc[u]);
+          if (lane == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = s;
+        }
+      }
+      TF_TICK(0);
+      __syncthreads();
+      TF_TICK(1);
+      if (tid < S - s0) {
+        const int slot = s0 + tid;
+        double y = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) y += spart[w * TF_MAXS + slot];
+        Xy[g + slot * G] = y;
+      }
+      // ================= exchange: arrive, wait for the other CTAs, load y and the raw column =================
+      TF_TICK(2);
+      __syncthreads();  // the y stores above and the raw stores of the sweep are ordered before the fence below
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        const unsigned target = (unsigned)G * (unsigned)(j + 1);
+        if (*reinterpret_cast<volatile unsigned*>(a.abort_flag) == 0u) {
+          const long long t0 = clock64();
+          int spins = 0;
+          while (tf_ld_acquire(ctr) < target) {
+            if ((++spins & 255) == 0 &&
+                (clock64() - t0 > 2000000000LL || *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)) {
+              atomicExch(a.abort_flag, 1u);
+              break;
+            }
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int r = tid + k * T;
+        const bool need = r >= first && r < n;
+        yv[k] = need ? tf_ld(Xy + r) : 0.0;
+        rv[k] = need ? tf_ld(Xr + r) : 0.0;
+      }
+    }
+    TF_TICK(3);
+    // ================= redundant O(n) part: w_j, updated column j+1, v_{j+1}, tau_{j+1} ========================
+    double part = 0.0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = tid + k * T;
+      if (r >= first && r < n) {
+        part = fma(yv[k], svc[r], part);
+        if (r == first) sbc[0] = yv[k];
+      }
+    }
+    const double pdot = tf_block_sum<T>(part, sred1);  // y^T v_j
+    TF_TICK(4);
+    const double alpha_w = 0.5 * tau_j * pdot;
+    const double w_first = tau_j * (sbc[0] - alpha_w);  // v_j[first] == 1
+    const int nf = first + 1;
+    double wv[KMAX], av2[KMAX];
+    part = 0.0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = tid + k * T;
+      wv[k] = 0.0; av2[k] = 0.0;
+      if (r >= first && r < n) {
+        const double vr = svc[r];
+        wv[k] = tau_j * (yv[k] - alpha_w * vr);
+        av2[k] = rv[k] - vr * w_first - wv[k];
+        if (r == first) {
+          if (g == 0) (a.d + q * n)[first] = av2[k];
+        } else if (r == nf) {
+          sbc[1] = av2[k];
+        } else {
+          part = fma(av2[k], av2[k], part);
+        }
+      }
+    }
+    const double xn2 = tf_block_sum<T>(part, sred2);
+    TF_TICK(5);
+    double beta = 0.0, tau_n = 0.0, scale = 0.0;
+    if (nf < n) {
+      householder_scalars(sbc[1], xn2, beta, tau_n, scale);
+      if (g == 0 && tid == 0) { (a.e + q * n)[first] = beta; (a.tau + q * n)[first] = tau_n; }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int r = tid + k * T;
+      if (r < n) {
+        const double vnew = r < nf ? 0.0 : (r == nf ? 1.0 : av2[k] * scale);
+        svn[r] = vnew;
+        sw[r] = wv[k];
+        // reflector j in LAPACK layout (below its unit entry).  Stored one step late: the exchange of step j
+        // proves that every CTA has finished reading column j as it came in (column 0 at j = -1 needs this).
+        if (j >= 0 && r > first && ((r >> 6) % G) == g) A[(size_t)j * lda + r] = svc[r];
+      }
+    }
+    __syncthreads();
+    TF_TICK(6);
+    double* t = svc; svc = svn; svn = t;
+    tau_j = tau_n;
+  }
+#ifdef GSCF_TF_DEBUG_TIMING
+  if ((tid == 0 || tid == T - 1) && (g == 0 || g == G - 1) && blockIdx.y == 0)
+    printf("cta %d tid %d cycles/col: sweep %lld sync %lld publish %lld poll %lld dot %lld norm %lld vec %lld loop %lld\n", g, tid,
+           tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
+#endif
+  if (g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
+    (a.d + q * n)[0] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+}  // namespace
+}  // namespace gscfb

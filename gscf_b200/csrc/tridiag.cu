@@ -36,6 +36,7 @@ struct TrdWs {
   unsigned* bar;        // [cap] group barrier counters of the persistent panel kernel
   double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
   double* SK;           // split-k partials: min(cap,16) * 16 * NBQ * n
+  double* X;            // [cap][4 np] exchange slots of the fused tridiagonalisation (trd_fused.cuh)
   int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
   double* Tf;           // [cap][NBQ*NBQ]
@@ -368,6 +369,7 @@ __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __re
 }  // namespace gscfb
 #include "trd_panel.cuh"
 #include "trd_cluster.cuh"
+#include "trd_fused.cuh"
 namespace gscfb {
 namespace {
 
@@ -397,9 +399,10 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.ypart = cv.take<double>((size_t)cap * ws.ncb * n);
   ws.pnorm = cv.take<double>((size_t)cap * ws.npart);
   ws.pdot = cv.take<double>((size_t)cap * ws.npart);
-  ws.bar = cv.take<unsigned>((size_t)cap);
+  ws.bar = cv.take<unsigned>((size_t)cap + 1);  // [cap] = abort flag of the fused kernel
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
   ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
+  ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
@@ -501,6 +504,133 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
   return GSCF_B200_OK;
 }
 
+// ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
+template <int KMAX, bool SMEM_A, int T>
+int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T>;
+  if (!configured) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G, cnt);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (cluster) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  } else {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GSCF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+  count_launch();
+  return GSCF_B200_OK;
+}
+
+template <int KMAX, bool SMEM_A, int T>
+int tf_max_clusters(int G, size_t smem) {
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G, 1);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int mc = 0;
+  if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return mc;
+}
+
+// returns -1 when the fused kernel does not cover the case (caller falls back to the panel kernels)
+int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
+                         cudaStream_t st) {
+  static int enabled = -1, sms = 0, g_single = 0, force_global = 0;
+  if (enabled < 0) {
+    const char* env = getenv("GSCF_B200_TRD_FUSED");
+    enabled = (env && env[0] == '0') ? 0 : 1;
+    int dev = 0, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || sms < 1) enabled = 0;
+    const char* ge = getenv("GSCF_B200_TF_G");
+    g_single = ge ? atoi(ge) : 0;
+    const char* fg = getenv("GSCF_B200_TF_GLOBAL");
+    force_global = (fg && fg[0] == '1') ? 1 : 0;
+  }
+  if (!enabled || n < 3 || (lda & 1) || n > 8192) return -1;
+  const int np = round_up(n, 2);
+  constexpr size_t kSmemMax = 220 * 1024;
+  const int g_slots = ceil_div(n, TF_MAXS);                       // S <= TF_MAXS
+  int g_smem = 0;                                                 // fewest CTAs with the columns in shared memory
+  if (!force_global && n <= 2048) {
+    for (int G = g_slots; G <= sms; ++G)
+      if (tf_smem_bytes(n, G, true) <= kSmemMax) { g_smem = G; break; }
+  }
+  // group size and launch mode
+  int G = 0;
+  bool cluster = false, smem_a = false;
+  if (g_smem > 0 && batch * g_smem > sms && g_smem <= 16) {
+    // more matrices than fit side by side: one thread-block cluster per matrix, scheduled by the hardware
+    G = g_smem <= 8 ? 8 : 16;
+    cluster = true; smem_a = true;
+  } else {
+    const int per = std::max(1, sms / std::max(1, std::min(batch, sms)));  // CTAs available per matrix
+    const int gmin = g_smem > 0 && g_smem <= per ? g_smem : g_slots;
+    if (gmin > sms) return -1;
+    G = std::max(gmin, std::min(per, ceil_div(n, 6)));
+    if (g_single > 0 && batch == 1) G = std::max(gmin, std::min(sms, g_single));
+    G = std::min(G, sms);
+    smem_a = g_smem > 0 && G >= g_smem;
+  }
+  const size_t smem = tf_smem_bytes(n, G, smem_a);
+  const int T = smem_a ? 256 : (n <= 4096 ? 512 : 1024);
+  const int K = ceil_div(n, T);
+  // (KMAX, SMEM_A, T) instantiations
+  auto launch = [&](const TfArgs& a, int cnt) -> int {
+    if (smem_a) {
+      if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
+      if (K <= 4) return tf_launch<4, true, 256>(a, G, cnt, cluster, smem, st);
+      return tf_launch<8, true, 256>(a, G, cnt, cluster, smem, st);
+    }
+    if (T == 512 && K <= 4) return tf_launch<4, false, 512>(a, G, cnt, cluster, smem, st);
+    if (T == 512) return tf_launch<8, false, 512>(a, G, cnt, cluster, smem, st);
+    return tf_launch<8, false, 1024>(a, G, cnt, cluster, smem, st);
+  };
+  if (cluster) {
+    int mc = K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
+                    : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
+    if (mc < 1) return -1;
+  }
+  TfArgs a;
+  a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = ws.d; a.e = ws.e; a.tau = ws.tau;
+  a.abort_flag = ws.bar + ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n;
+  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)ws.cap + 1) * sizeof(unsigned), st));
+  phase_mark(PH_SYMV_SAMPLE, true, st);
+  const int per_launch = cluster ? 32768 : std::max(1, sms / G);
+  for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
+    a.mat0 = mat0;
+    GSCF_TRY(launch(a, std::min(per_launch, batch - mat0)));
+  }
+  phase_mark(PH_SYMV_SAMPLE, false, st);
+  return GSCF_B200_OK;
+}
+
 // Persistent-panel driver: one cooperative launch per panel + the deferred rank-2k GEMM update.
 int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                    cudaStream_t st) {
@@ -519,6 +649,10 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
     if (!coop || capacity < 1) legacy = 1;
   }
   if (legacy || n < 3) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
+  {
+    const int fs = tridiagonalise_fused(n, A, lda, sA, ws, batch, map, st);
+    if (fs >= 0) return fs;
+  }
   // ---- thread-block-cluster path for L2-resident matrices ------------------------------------------
   static int cluster_mode = -1;  // 1: available, 0: unavailable / disabled
   if (cluster_mode < 0) {
