@@ -173,23 +173,116 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
   int* rot_b = ws.rot_b + q * n + lo;
   double* rot_c = ws.rot_c + q * n + lo;
   double* rot_s = ws.rot_s + q * n + lo;
-  if (threadIdx.x == 0) {
-    int K = 0, nrot = 0;
-    dc_deflate(k, sd, sz, rho, sidx, sct, &K, sdl, sw, snd, sdc, &nrot, rot_a, rot_b, rot_c, rot_s);
-    // group the poles by column type: [1 | 2 | 3]
-    int c1 = 0, c2 = 0, c3 = 0;
-    for (int p = 0; p < K; ++p) {
-      const int ty = sct[snd[p]];
-      c1 += ty == 1; c2 += ty == 2; c3 += ty == 3;
+  // ---- deflation.  Fast path (all threads): entries with a negligible z component deflate, the others become
+  // poles in sorted order, provided no pair of neighbouring poles is close enough for a Givens rotation
+  // (dlaed2's second test).  A rotation changes z and d of the pair, which feeds the test of the next pair,
+  // so as soon as one is needed thread 0 redoes the merge with the sequential dc_deflate.
+  __shared__ double s_red[32];
+  __shared__ int s_scan[32];
+  __shared__ int s_any;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+  auto block_max = [&](double v) {
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    double m = 0.0;
+    for (int w = 0; w < nwarp; ++w) m = fmax(m, s_red[w]);
+    return m;
+  };
+  // exclusive scan of one int per thread over the block; *total = sum
+  auto block_scan = [&](int v, int* total) {
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    int o1 = 0, o2 = c1, o3 = c1 + c2;
-    for (int p = 0; p < K; ++p) {
-      const int ty = sct[snd[p]];
-      gpos[p] = ty == 1 ? o1++ : (ty == 2 ? o2++ : o3++);
+    __syncthreads();
+    if (lane == 31) s_scan[wid] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int w = 0; w < nwarp; ++w) {
+      const int c = s_scan[w];
+      if (w < wid) base += c;
+      tot += c;
     }
-    s_K = K; s_nrot = nrot; s_c[0] = c1; s_c[1] = c2; s_c[2] = c3;
-    meta[0] = K; meta[1] = nrot; meta[2] = c1; meta[3] = c2; meta[4] = c3;
-    (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
+    *total = tot;
+    return base + inc - v;
+  };
+  double dmx = 0.0, zmx = 0.0;
+  for (int j = tid; j < k; j += blockDim.x) { dmx = fmax(dmx, fabs(sd[j])); zmx = fmax(zmx, fabs(sz[j])); }
+  dmx = block_max(dmx);
+  zmx = block_max(zmx);
+  const double tol = 8.0 * kDcEps * fmax(dmx, zmx);
+  if (tid == 0) s_any = 0;
+  // contiguous chunk of sorted positions per thread
+  const int per = (k + blockDim.x - 1) / blockDim.x;
+  const int j_lo = min(k, tid * per), j_hi = min(k, j_lo + per);
+  int cnt = 0;
+  for (int jj = j_lo; jj < j_hi; ++jj) cnt += (rho * fabs(sz[sidx[jj]]) > tol) ? 1 : 0;
+  int Kp = 0;
+  int pos = block_scan(cnt, &Kp);
+  const bool all_deflated = rho * zmx <= tol;
+  if (all_deflated) Kp = 0;
+  {
+    int ppos = pos;
+    for (int jj = j_lo; jj < j_hi; ++jj) {
+      const int nj = sidx[jj];
+      if (!all_deflated && rho * fabs(sz[nj]) > tol) snd[ppos++] = nj;
+      else sdc[jj - (all_deflated ? 0 : ppos)] = nj;
+    }
+  }
+  __syncthreads();
+  for (int pp = 1 + tid; pp < Kp; pp += blockDim.x) {
+    const int pj = snd[pp - 1], nj = snd[pp];
+    double sv = sz[pj], cv = sz[nj];
+    const double tau = hypot(cv, sv);
+    const double t = sd[nj] - sd[pj];
+    cv /= tau;
+    sv = -sv / tau;
+    if (fabs(t * cv * sv) <= tol) s_any = 1;
+  }
+  __syncthreads();
+  if (s_any) {
+    if (threadIdx.x == 0) {
+      int K = 0, nrot = 0;
+      dc_deflate(k, sd, sz, rho, sidx, sct, &K, sdl, sw, snd, sdc, &nrot, rot_a, rot_b, rot_c, rot_s);
+      // group the poles by column type: [1 | 2 | 3]
+      int c1 = 0, c2 = 0, c3 = 0;
+      for (int p = 0; p < K; ++p) {
+        const int ty = sct[snd[p]];
+        c1 += ty == 1; c2 += ty == 2; c3 += ty == 3;
+      }
+      int o1 = 0, o2 = c1, o3 = c1 + c2;
+      for (int p = 0; p < K; ++p) {
+        const int ty = sct[snd[p]];
+        gpos[p] = ty == 1 ? o1++ : (ty == 2 ? o2++ : o3++);
+      }
+      s_K = K; s_nrot = nrot; s_c[0] = c1; s_c[1] = c2; s_c[2] = c3;
+      meta[0] = K; meta[1] = nrot; meta[2] = c1; meta[3] = c2; meta[4] = c3;
+      (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
+    }
+  } else {
+    // poles in sorted order; stable partition by column type (1: top rows, 3: bottom rows; no rotations -> no type 2)
+    const int pper = (Kp + blockDim.x - 1) / blockDim.x;
+    const int p_lo = min(Kp, tid * pper), p_hi = min(Kp, p_lo + pper);
+    int c1l = 0;
+    for (int pp = p_lo; pp < p_hi; ++pp) {
+      const int nj = snd[pp];
+      sdl[pp] = sd[nj];
+      sw[pp] = sz[nj];
+      c1l += sct[nj] == 1 ? 1 : 0;
+    }
+    int c1 = 0;
+    int o1 = block_scan(c1l, &c1);
+    int o3 = c1 + (p_lo - o1);
+    for (int pp = p_lo; pp < p_hi; ++pp) gpos[pp] = sct[snd[pp]] == 1 ? o1++ : o3++;
+    if (tid == 0) {
+      s_K = Kp; s_nrot = 0; s_c[0] = c1; s_c[1] = 0; s_c[2] = Kp - c1;
+      meta[0] = Kp; meta[1] = 0; meta[2] = c1; meta[3] = 0; meta[4] = Kp - c1;
+      (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
+    }
   }
   __syncthreads();
   const int K = s_K, nrot = s_nrot;

@@ -120,6 +120,7 @@ trd_fused_kernel(const TfArgs a) {
 
 #ifdef GSCF_TF_DEBUG_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tbucket[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tmark = clock64();
 #define TF_TICK(k) do { const long long _t = clock64(); tacc[k] += _t - tmark; tmark = _t; } while (0)
 #else
@@ -188,12 +189,32 @@ trd_fused_kernel(const TfArgs a) {
             }
           }
         }
+        {
+          // 8 sums over the warp with 7 exchanges instead of 40: every butterfly step halves the number of values a
+          // lane is responsible for (SHFL issues at one warp per clock per SM - 80 of them per warp dominated the sweep)
+          static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          double a4[4], a2[2];
 #pragma unroll
-        for (int u = 0; u < TF_CG; ++u) {
-          const double s = warp_sum(acc[u]);
-          if (lane == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = s;
+          for (int i = 0; i < 4; ++i) {
+            const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+          const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+          if ((lane & 3) == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = a1;
         }
       }
+#ifdef GSCF_TF_DEBUG_TIMING
+      if (j >= 0) tbucket[(j * 16) / n] += clock64() - tmark;
+#endif
       TF_TICK(0);
       __syncthreads();
       TF_TICK(1);
@@ -295,6 +316,11 @@ trd_fused_kernel(const TfArgs a) {
   if ((tid == 0 || tid == T - 1) && (g == 0 || g == G - 1) && blockIdx.y == 0)
     printf("cta %d tid %d cycles/col: sweep %lld sync %lld publish %lld poll %lld dot %lld norm %lld vec %lld loop %lld\n", g, tid,
            tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
+  if (tid == 0 && g == 0 && blockIdx.y == 0) {
+    printf("sweep cycles/col by sixteenth of the reduction:");
+    for (int b = 0; b < 16; ++b) printf(" %lld", tbucket[b] * 16 / n);
+    printf("\n");
+  }
 #endif
   if (g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
     (a.d + q * n)[0] = __longlong_as_double(0x7ff8000000000000LL);

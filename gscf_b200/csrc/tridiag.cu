@@ -37,6 +37,8 @@ struct TrdWs {
   double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
   double* SK;           // split-k partials: min(cap,16) * 16 * NBQ * n
   double* X;            // [cap][4 np] exchange slots of the fused tridiagonalisation (trd_fused.cuh)
+  double* VPW;          // [cap][2][32][np] pending reflector panels of the blocked fused kernel
+  double* PQ;           // [cap][2][256][64] partial dots of the blocked fused kernel
   int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
   double* Tf;           // [cap][NBQ*NBQ]
@@ -287,10 +289,12 @@ __global__ void extract_v_kernel(const double* __restrict__ Ab, int lda, long lo
   (void)pw;
 }
 
-// T (pw x pw upper triangular, dlarft forward/columnwise) from G = V^T V and tau
-__global__ void larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ map) {
+// T (pw x pw upper triangular, dlarft forward/columnwise) from G = V^T V and tau:
+//   T(0:j, j) = -tau_j T(0:j, 0:j) G(0:j, j),  T(j, j) = tau_j.
+// One CTA per matrix, 4 threads per row of T share the dot product of every step.
+__global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ map) {
   extern __shared__ double sm[];
-  double* T = sm;             // pw*pw
+  double* T = sm;             // pw*pw, column-major
   double* G = sm + pw * pw;   // pw*pw
   const long long q = map ? map[blockIdx.x] : blockIdx.x;
   const double* Gg = ws.Gm + q * NBQ * NBQ;
@@ -300,16 +304,18 @@ __global__ void larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ m
     G[idx] = Gg[idx];  // ld = pw (written by the GEMM with ldc = pw)
   }
   __syncthreads();
+  const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
   for (int j = 0; j < pw; ++j) {
     const double tj = tau[j];
-    // T(0:j, j) = -tau_j * T(0:j, 0:j) * G(0:j, j)
-    if (threadIdx.x < j) {
-      const int r = threadIdx.x;
-      double s = 0.0;
-      for (int k = r; k < j; ++k) s += T[(size_t)k * pw + r] * G[(size_t)j * pw + k];
-      T[(size_t)j * pw + r] = -tj * s;
+    double s = 0.0;
+    if (r < j)
+      for (int k = r + part; k < j; k += 4) s = fma(T[(size_t)k * pw + r], G[(size_t)j * pw + k], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) {
+      if (r < j) T[(size_t)j * pw + r] = -tj * s;
+      else if (r == j) T[(size_t)j * pw + j] = tj;
     }
-    if (threadIdx.x == j) T[(size_t)j * pw + j] = tj;
     __syncthreads();
   }
   double* Tg = ws.Tf + q * NBQ * NBQ;
@@ -370,6 +376,7 @@ __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __re
 #include "trd_panel.cuh"
 #include "trd_cluster.cuh"
 #include "trd_fused.cuh"
+#include "trd_fused_blk.cuh"
 namespace gscfb {
 namespace {
 
@@ -399,7 +406,9 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.ypart = cv.take<double>((size_t)cap * ws.ncb * n);
   ws.pnorm = cv.take<double>((size_t)cap * ws.npart);
   ws.pdot = cv.take<double>((size_t)cap * ws.npart);
-  ws.bar = cv.take<unsigned>((size_t)cap + 1);  // [cap] = abort flag of the fused kernel
+  ws.bar = cv.take<unsigned>((size_t)2 * cap + 1);  // [0,cap) y counters, [cap,2cap) partial-dot counters, [2cap] abort flag
+  ws.VPW = cv.take<double>((size_t)cap * 2 * 32 * round_up(n, 2));
+  ws.PQ = cv.take<double>((size_t)cap * 2 * 256 * 64);
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
   ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
   ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
@@ -534,6 +543,34 @@ int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaSt
   return GSCF_B200_OK;
 }
 
+template <int KMAX, int T>
+int tfb_launch_t(const TfbArgs& a, int G, int cnt, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = trd_fused_blocked_kernel<KMAX, T>;
+  if (!configured) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G, cnt);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GSCF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+  count_launch();
+  return GSCF_B200_OK;
+}
+int tfb_launch(const TfbArgs& a, int G, int cnt, int T, int K, size_t smem, cudaStream_t st) {
+  if (T == 512 && K <= 4) return tfb_launch_t<4, 512>(a, G, cnt, smem, st);
+  if (T == 512) return tfb_launch_t<8, 512>(a, G, cnt, smem, st);
+  return tfb_launch_t<8, 1024>(a, G, cnt, smem, st);
+}
+
 template <int KMAX, bool SMEM_A, int T>
 int tf_max_clusters(int G, size_t smem) {
   auto kern = trd_fused_kernel<KMAX, SMEM_A, T>;
@@ -554,6 +591,14 @@ int tf_max_clusters(int G, size_t smem) {
   int mc = 0;
   if (cudaOccupancyMaxActiveClusters(&mc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return mc;
+}
+
+// trailing order below which deferring the rank-2 updates stops paying (measured on B200: n = 4096 eigensolve 120.5 ms
+// unblocked, 111.5 ms always blocked, 108.4 ms with the switch at 2500)
+int tf_unblocked_below() {
+  static int ub = -1;
+  if (ub < 0) { const char* ue = getenv("GSCF_B200_TF_UNBLOCKED_BELOW"); ub = ue ? atoi(ue) : 2500; }
+  return ub;
 }
 
 // returns -1 when the fused kernel does not cover the case (caller falls back to the panel kernels)
@@ -599,11 +644,14 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     smem_a = g_smem > 0 && G >= g_smem;
   }
   const size_t smem = tf_smem_bytes(n, G, smem_a);
-  const int T = smem_a ? 256 : (n <= 4096 ? 512 : 1024);
+  static int t_small = -1;
+  if (t_small < 0) { const char* te = getenv("GSCF_B200_TF_T"); t_small = te ? atoi(te) : 256; }
+  const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : (n <= 4096 ? 512 : 1024);
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
     if (smem_a) {
+      if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
       if (K <= 4) return tf_launch<4, true, 256>(a, G, cnt, cluster, smem, st);
       return tf_launch<8, true, 256>(a, G, cnt, cluster, smem, st);
@@ -612,20 +660,33 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     if (T == 512) return tf_launch<8, false, 512>(a, G, cnt, cluster, smem, st);
     return tf_launch<8, false, 1024>(a, G, cnt, cluster, smem, st);
   };
+  static int blocked = -1;
+  if (blocked < 0) { const char* be = getenv("GSCF_B200_TF_BLOCKED"); blocked = (be && be[0] == '0') ? 0 : 1; }
+  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below();
   if (cluster) {
-    int mc = K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
+    int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
                     : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
     if (mc < 1) return -1;
   }
   TfArgs a;
   a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = ws.d; a.e = ws.e; a.tau = ws.tau;
-  a.abort_flag = ws.bar + ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n;
-  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)ws.cap + 1) * sizeof(unsigned), st));
+  a.abort_flag = ws.bar + 2 * ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n;
+  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)2 * ws.cap + 1) * sizeof(unsigned), st));
   phase_mark(PH_SYMV_SAMPLE, true, st);
   const int per_launch = cluster ? 32768 : std::max(1, sms / G);
   for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
     a.mat0 = mat0;
-    GSCF_TRY(launch(a, std::min(per_launch, batch - mat0)));
+    const int cnt = std::min(per_launch, batch - mat0);
+    if (use_blocked) {
+      TfbArgs ab;
+      ab.b = a; ab.VP = ws.VPW; ab.WP = ws.VPW + (size_t)ws.cap * 32 * np; ab.PQ = ws.PQ; ab.ctr2 = ws.bar + ws.cap;
+      {
+        ab.unblocked_below = tf_unblocked_below();
+      }
+      GSCF_TRY(tfb_launch(ab, G, cnt, T, K, tfb_smem_bytes(n), st));
+    } else {
+      GSCF_TRY(launch(a, cnt));
+    }
   }
   phase_mark(PH_SYMV_SAMPLE, false, st);
   return GSCF_B200_OK;
@@ -769,11 +830,13 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     GemmParams y = gemm_params(pw, n, m, 1.0, ws.Vc, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
     y.sA = (long long)ws.ld * NBQ; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
     GSCF_TRY(launch_gemm_splitk(true, false, y, batch, std::min(splits, 8), ws.SK, st));
-    // Y2 = T Y by back substitution with T^-1 = diag(1/tau) + striu(G)
-    wy_trsm_kernel<NBQ><<<dim3(ceil_div(n, 128), batch), 128, (NBQ * (NBQ + 1) + NBQ * 128) * sizeof(double), st>>>(
-        ws, j0, pw, n, map);
+    // T from G and tau (dlarft), Y2 = T Y
+    larft_kernel<<<batch, 256, 2 * NBQ * NBQ * sizeof(double), st>>>(ws, j0, pw, map);
     count_launch();
     GSCF_CHECK_LAUNCH();
+    GemmParams t2 = gemm_params(pw, n, pw, 1.0, ws.Tf, pw, ws.Yw, NBQ, 0.0, ws.Y2, NBQ);
+    t2.sA = NBQ * NBQ; t2.sB = t2.sC = (long long)NBQ * n; t2.batch_map = map;
+    GSCF_TRY(launch_gemm(false, false, t2, batch, pw, n, st));
     // Z(j0+1:, :) -= Vc Y2
     GemmParams u = gemm_params(m, n, pw, -1.0, ws.Vc, ws.ld, ws.Y2, NBQ, 1.0, Z + j0 + 1, ldz);
     u.sA = (long long)ws.ld * NBQ; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;

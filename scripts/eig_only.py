@@ -20,7 +20,7 @@ for b in range(batch):
         a = rng.standard_normal((n, n)); a = a + a.T
         if b == 1:  # clustered spectrum / deflation-heavy
             q, _ = np.linalg.qr(rng.standard_normal((n, n)))
-            a = (q * np.repeat(np.arange(max(1, n // 8)), 8)[:n]) @ q.T
+            a = (q * np.repeat(np.arange(n // 8 + 1), 8)[:n]) @ q.T
             a = 0.5 * (a + a.T)
         mats.append(a)
     else:

@@ -4,7 +4,7 @@ import torch
 from gscf_b200 import lib as L
 for (m, n, k, ta, tb) in [(4096, 4096, 4096, 0, 0), (4096, 4096, 4096, 0, 1), (4096, 4096, 4096, 1, 0), (4096, 4096, 512, 0, 1),
                           (4096, 4096, 64, 0, 1), (1024, 1024, 1024, 0, 0), (1024, 1024, 128, 0, 1), (2048, 2048, 2048, 0, 0),
-                          (8192, 8192, 2048, 0, 0)]:
+                          (8192, 8192, 2048, 0, 0), (64, 4096, 4096, 1, 0), (4096, 4096, 64, 0, 0), (2048, 4096, 64, 0, 0), (4096, 512, 4096, 0, 0), (4096, 4096, 512, 0, 0)]:
     A = torch.randn(m * k, dtype=torch.float64, device="cuda")
     B = torch.randn(k * n, dtype=torch.float64, device="cuda")
     Cm = torch.zeros(m * n, dtype=torch.float64, device="cuda")

@@ -28,6 +28,7 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["c2"]
     if "c2" in which: run(1024, 128, 64, 8)
     if "c3" in which: run(4096, 512, 64, 10, reps=1)
-    if "c4" in which: run(128, 16, 8, 4, P=512)
+    if "c4" in which: run(128, 16, 8, 4, P=4096)
+    if "c5full" in which: run(512, 64, 32, 4, P=256, n_beta=60, reps=1)
     if "c5" in which: run(512, 64, 32, 4, P=16, n_beta=60)
     if "mid" in which: run(512, 64, 32, 8)
