@@ -41,6 +41,12 @@ struct TrdWs {
   double* PQ;           // [cap][2][256][64] partial dots of the blocked fused kernel
   int npart;            // entries per matrix in pnorm / pdot
   double* Vc;           // [cap][ld*NBQ]
+  double* Vf;           // [cap][ld*n]  all reflectors, unit lower trapezoidal, zeros above
+  double* Wf;           // [cap][ld*n]  V_b T_b per block of NBQ reflectors
+  double* Gall;         // [cap][nbq][NBQ*NBQ]  V_b^T V_b
+  double* Tall;         // [cap][nbq][NBQ*NBQ]  T_b
+  GemmDesc* bdesc;      // [cap][nbq] descriptors of the per-block set-up GEMMs
+  int nbq;              // blocks of NBQ reflectors
   double* Tf;           // [cap][NBQ*NBQ]
   double* Gm;           // [cap][NBQ*NBQ]
   double* Yw;           // [cap][NBQ*n]
@@ -289,37 +295,48 @@ __global__ void extract_v_kernel(const double* __restrict__ Ab, int lda, long lo
   (void)pw;
 }
 
-// T (pw x pw upper triangular, dlarft forward/columnwise) from G = V^T V and tau:
-//   T(0:j, j) = -tau_j T(0:j, 0:j) G(0:j, j),  T(j, j) = tau_j.
-// One CTA per matrix, 4 threads per row of T share the dot product of every step.
-__global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, int j0, int pw, const int* __restrict__ map) {
+// T (pw x pw upper triangular, the dlarft factor) from G = V^T V and tau through T^-1 = diag(1/tau) + striu(G):
+// column c of T solves the triangular system by back substitution,
+//   T(c,c) = tau_c,   T(r,c) = -tau_r sum_{k=r+1..c} G(r,k) T(k,c),   r = c-1 .. 0
+// (tau_r = 0, i.e. H_r = I, gives a zero row and column, as dlarft does).  The columns are independent: one quad
+// of threads per column, no block-wide barrier inside the recurrence.
+__global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, const int* __restrict__ map) {
   extern __shared__ double sm[];
-  double* T = sm;             // pw*pw, column-major
-  double* G = sm + pw * pw;   // pw*pw
-  const long long q = map ? map[blockIdx.x] : blockIdx.x;
-  const double* Gg = ws.Gm + q * NBQ * NBQ;
-  const double* tau = ws.tau + q * ws.n + j0;
+  constexpr int LDT = NBQ + 1;
+  double* Gt = sm;                 // Gt[r*LDT + k] = G(r,k)
+  double* X = sm + NBQ * LDT;      // X[c*LDT + k] = T(k,c)
+  __shared__ double stau[NBQ];
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const int b = blockIdx.x, j0 = b * NBQ, pw = min(NBQ, ws.n - 1 - j0);
+  const double* Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw
   for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
-    T[idx] = 0.0;
-    G[idx] = Gg[idx];  // ld = pw (written by the GEMM with ldc = pw)
+    const int k = idx / pw, r = idx - k * pw;
+    Gt[r * LDT + k] = Gg[idx];
+  }
+  for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = (ws.tau + q * ws.n + j0)[idx];
+  __syncthreads();
+  const int c = threadIdx.x >> 2, part = threadIdx.x & 3;
+  double* x = X + c * LDT;
+  const unsigned qmask = 0xFu << (threadIdx.x & 28);  // the four lanes of my quad: quads of a warp run different trip counts
+  if (c < pw) {
+    if (part == 0) x[c] = stau[c];
+    __syncwarp(qmask);
+    for (int r = c - 1; r >= 0; --r) {
+      const double* g = Gt + r * LDT;
+      double s = 0.0;
+      for (int k = r + 1 + part; k <= c; k += 4) s = fma(g[k], x[k], s);
+      s += __shfl_xor_sync(qmask, s, 1);
+      s += __shfl_xor_sync(qmask, s, 2);
+      if (part == 0) x[r] = -stau[r] * s;
+      __syncwarp(qmask);
+    }
   }
   __syncthreads();
-  const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
-  for (int j = 0; j < pw; ++j) {
-    const double tj = tau[j];
-    double s = 0.0;
-    if (r < j)
-      for (int k = r + part; k < j; k += 4) s = fma(T[(size_t)k * pw + r], G[(size_t)j * pw + k], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (part == 0) {
-      if (r < j) T[(size_t)j * pw + r] = -tj * s;
-      else if (r == j) T[(size_t)j * pw + j] = tj;
-    }
-    __syncthreads();
+  double* Tg = ws.Tall + (q * ws.nbq + b) * NBQ * NBQ;
+  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
+    const int cc = idx / pw, r = idx - cc * pw;
+    Tg[idx] = r <= cc ? X[cc * LDT + r] : 0.0;
   }
-  double* Tg = ws.Tf + q * NBQ * NBQ;
-  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) Tg[idx] = T[idx];
 }
 
 // Y2 = T Y without forming T: T^-1 = diag(1/tau) + striu(V^T V) (upper triangular), so the rows of
@@ -415,6 +432,12 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
+  ws.nbq = std::max(1, ceil_div(n - 1, NBQ));
+  ws.Vf = cv.take<double>((size_t)cap * ld * n);
+  ws.Wf = cv.take<double>((size_t)cap * ld * n);
+  ws.Gall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
+  ws.Tall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
+  ws.bdesc = cv.take<GemmDesc>((size_t)cap * ws.nbq);
   ws.Tf = cv.take<double>((size_t)cap * NBQ * NBQ);
   ws.Gm = cv.take<double>((size_t)cap * NBQ * NBQ);
   ws.Yw = cv.take<double>((size_t)cap * NBQ * n);
@@ -807,39 +830,80 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
   return GSCF_B200_OK;
 }
 
-// Z <- Q Z with the reflectors stored in A / tau.
+// ---- back-transformation ---------------------------------------------------------------------------------------
+// All reflectors as a unit lower trapezoidal matrix with explicit zeros: Vf(:, c) = [0 .. 0, 1, v_c], unit at row c+1.
+__global__ void extract_v_all_kernel(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws,
+                                     const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.z] : blockIdx.z;
+  const int n = ws.n, c = blockIdx.y;
+  const double* a = Ab + q * sA + (size_t)c * lda;
+  double* v = ws.Vf + q * (long long)ws.ld * n + (size_t)c * ws.ld;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    v[r] = (c >= n - 1 || r <= c) ? 0.0 : (r == c + 1 ? 1.0 : a[r]);
+}
+
+// descriptors of the per-block set-up GEMMs: which = 0: G_b = V_b^T V_b,  1: W_b = V_b T_b
+__global__ void bt_desc_kernel(TrdWs ws, int which, int batch, const int* __restrict__ map) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * ws.nbq) return;
+  const int z = idx / ws.nbq, b = idx - z * ws.nbq;
+  const long long q = map ? map[z] : z;
+  const int n = ws.n, j0 = b * NBQ, pw = min(NBQ, n - 1 - j0), m = n - j0 - 1;
+  const double* Vb = ws.Vf + q * (long long)ws.ld * n + (size_t)j0 * ws.ld + j0 + 1;
+  GemmDesc d;
+  if (which == 0) {
+    d.A = Vb; d.lda = ws.ld; d.B = Vb; d.ldb = ws.ld;
+    d.C = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ; d.ldc = pw;
+    d.m = pw; d.n = pw; d.k = m;
+  } else {
+    d.A = Vb; d.lda = ws.ld; d.B = ws.Tall + (q * ws.nbq + b) * NBQ * NBQ; d.ldb = pw;
+    d.C = ws.Wf + q * (long long)ws.ld * n + (size_t)j0 * ws.ld + j0 + 1; d.ldc = ws.ld;
+    d.m = m; d.n = pw; d.k = pw;
+  }
+  d.alpha = 1.0; d.beta = 0.0;
+  ws.bdesc[idx] = d;
+}
+
+// Z <- Q Z with the reflectors stored in A / tau:  Q = H(0) .. H(n-2) = prod_b (I - V_b T_b V_b^T).
+// Everything that does not depend on Z is done up front for all blocks at once (V, G_b, T_b, W_b = V_b T_b: four
+// launches); the sequential part is two GEMMs per block:  Y = V_b^T Z,  Z -= W_b Y.
 int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& ws, double* Z, int ldz,
                    long long sZ, int batch, const int* map, cudaStream_t st) {
   if (n < 2) return GSCF_B200_OK;
   const int nref = n - 1;  // reflectors 0..n-2
-  const int nblocks = ceil_div(nref, NBQ);
+  const int nblocks = ws.nbq;
+  extract_v_all_kernel<<<dim3(std::max(1, std::min(8, ceil_div(n, 256))), n, batch), 256, 0, st>>>(A, lda, sA, ws, map);
+  bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 0, batch, map);
+  count_launch(2);
+  GSCF_CHECK_LAUNCH();
+  {
+    GemmParams gp{};
+    gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
+    GSCF_TRY(launch_gemm(true, false, gp, batch * nblocks, NBQ, NBQ, st));
+  }
+  larft_kernel<<<dim3(nblocks, batch), 256, 2 * NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);
+  bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 1, batch, map);
+  count_launch(2);
+  GSCF_CHECK_LAUNCH();
+  {
+    GemmParams gp{};
+    gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
+    GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, NBQ, st));
+  }
   for (int b = nblocks - 1; b >= 0; --b) {
     const int j0 = b * NBQ;
     const int pw = std::min(NBQ, nref - j0);
     const int m = n - j0 - 1;  // rows j0+1 .. n-1
-    extract_v_kernel<<<dim3(std::max(1, std::min(64, ceil_div(m, 256))), pw, batch), 256, 0, st>>>(A, lda, sA, ws, j0,
-                                                                                               pw, map);
-    count_launch();
-    GSCF_CHECK_LAUNCH();
-    // G = Vc^T Vc  (pw x pw, ld pw)
-    GemmParams g = gemm_params(pw, pw, m, 1.0, ws.Vc, ws.ld, ws.Vc, ws.ld, 0.0, ws.Gm, pw);
-    g.sA = g.sB = (long long)ws.ld * NBQ; g.sC = NBQ * NBQ; g.batch_map = map;
-    const int splits = batch >= 16 ? 1 : std::max(1, std::min(16, m / 128));  // long-k TN products: split-k
-    GSCF_TRY(launch_gemm_splitk(true, false, g, batch, splits, ws.SK, st));
-    // Y = Vc^T Z(j0+1:, :)   (pw x n, ld NBQ)
-    GemmParams y = gemm_params(pw, n, m, 1.0, ws.Vc, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
-    y.sA = (long long)ws.ld * NBQ; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
-    GSCF_TRY(launch_gemm_splitk(true, false, y, batch, std::min(splits, 8), ws.SK, st));
-    // T from G and tau (dlarft), Y2 = T Y
-    larft_kernel<<<batch, 256, 2 * NBQ * NBQ * sizeof(double), st>>>(ws, j0, pw, map);
-    count_launch();
-    GSCF_CHECK_LAUNCH();
-    GemmParams t2 = gemm_params(pw, n, pw, 1.0, ws.Tf, pw, ws.Yw, NBQ, 0.0, ws.Y2, NBQ);
-    t2.sA = NBQ * NBQ; t2.sB = t2.sC = (long long)NBQ * n; t2.batch_map = map;
-    GSCF_TRY(launch_gemm(false, false, t2, batch, pw, n, st));
-    // Z(j0+1:, :) -= Vc Y2
-    GemmParams u = gemm_params(m, n, pw, -1.0, ws.Vc, ws.ld, ws.Y2, NBQ, 1.0, Z + j0 + 1, ldz);
-    u.sA = (long long)ws.ld * NBQ; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;
+    const double* Vb = ws.Vf + (size_t)j0 * ws.ld + j0 + 1;
+    const double* Wb = ws.Wf + (size_t)j0 * ws.ld + j0 + 1;
+    // Y = V_b^T Z(j0+1:, :)   (pw x n, ld NBQ)
+    GemmParams y = gemm_params(pw, n, m, 1.0, Vb, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
+    y.sA = (long long)ws.ld * n; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
+    const int splits = batch >= 16 ? 1 : std::max(1, std::min(8, m / 128));  // long-k TN product: split-k
+    GSCF_TRY(launch_gemm_splitk(true, false, y, batch, splits, ws.SK, st));
+    // Z(j0+1:, :) -= W_b Y
+    GemmParams u = gemm_params(m, n, pw, -1.0, Wb, ws.ld, ws.Yw, NBQ, 1.0, Z + j0 + 1, ldz);
+    u.sA = (long long)ws.ld * n; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;
     GSCF_TRY(launch_gemm(false, false, u, batch, m, n, st));
   }
   return GSCF_B200_OK;
@@ -868,7 +932,7 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   static bool cfg = false;
   if (!cfg) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       2 * NBQ * NBQ * (int)sizeof(double)));
+                                       2 * NBQ * (NBQ + 1) * (int)sizeof(double)));
     GSCF_CUDA_TRY(cudaFuncSetAttribute(wy_trsm_kernel<NBQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (NBQ * (NBQ + 1) + NBQ * 128) * (int)sizeof(double)));
     cfg = true;
