@@ -17,7 +17,7 @@ namespace gscfb {
 
 constexpr int kJacobiMaxSweeps = 40;
 
-template <int NPL>
+template <int NPL, int PPW>
 __global__ void __launch_bounds__(1024)
 jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long strideA,
                        double* __restrict__ w, long long stride_w, double* __restrict__ Z,
@@ -65,50 +65,99 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
 
   const double tol = sqrt((double)n) * 2.220446049250313e-16;
   const int npairs = ne >> 1;
+  // Every step has three phases separated by block barriers:
+  //   1. one warp per column pair: a = |g_p|^2, b = |g_q|^2, c = g_p.g_q (columns stay in registers)
+  //   2. one THREAD per pair: rotation angle (sqrt / divisions).  Done per warp this scalar chain is ~100 FP64
+  //      instructions executed 32-fold redundantly and it saturated the FP64 pipe (64 lanes / clock / SM on B200)
+  //   3. the warps apply the rotations from registers
+  // PPW = pairs per warp (template): 1 for n <= 64, 2 for n <= 128, 3 for n <= 160 (32 warps)
+  __shared__ double s_a[kJacobiMaxN / 2 + 1], s_b[kJacobiMaxN / 2 + 1], s_c[kJacobiMaxN / 2 + 1];
+  __shared__ double s_cs[kJacobiMaxN / 2 + 1], s_sn[kJacobiMaxN / 2 + 1];
   int sweeps = 0;
   bool converged = false;
   for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
     int rotated = 0;
     for (int step = 0; step < ne - 1; ++step) {
-      for (int pr = warp; pr < npairs; pr += nwarp) {
-        // round-robin tournament: index ne-1 is fixed, the others rotate
-        int p, q;
-        if (pr == 0) {
-          p = ne - 1;
-          q = step;
-        } else {
-          p = (step + pr) % (ne - 1);
-          q = (step - pr + (ne - 1)) % (ne - 1);
-        }
-        if (p > q) { const int t = p; p = q; q = t; }
-        double* gp = G + (size_t)p * ldg;
-        double* gq = G + (size_t)q * ldg;
-        double xp[NPL], xq[NPL];
-        double a = 0.0, b = 0.0, c = 0.0;
+      double xp[PPW][NPL], xq[PPW][NPL];
+      int pp[PPW], qq[PPW];
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int r = lane + 32 * i;
-          xp[i] = r < n ? gp[r] : 0.0;
-          xq[i] = r < n ? gq[r] : 0.0;
-          a = fma(xp[i], xp[i], a);
-          b = fma(xq[i], xq[i], b);
-          c = fma(xp[i], xq[i], c);
+      for (int u = 0; u < PPW; ++u) {
+        const int pr = warp + u * nwarp;
+        pp[u] = -1; qq[u] = -1;
+        if (pr < npairs) {
+          // round-robin tournament: index ne-1 is fixed, the others rotate
+          int p, q;
+          if (pr == 0) {
+            p = ne - 1;
+            q = step;
+          } else {
+            p = (step + pr) % (ne - 1);
+            q = (step - pr + (ne - 1)) % (ne - 1);
+          }
+          if (p > q) { const int t = p; p = q; q = t; }
+          pp[u] = p; qq[u] = q;
+          const double* gp = G + (size_t)p * ldg;
+          const double* gq = G + (size_t)q * ldg;
+          double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll
+          for (int i = 0; i < NPL; ++i) {
+            const int r = lane + 32 * i;
+            xp[u][i] = r < n ? gp[r] : 0.0;
+            xq[u][i] = r < n ? gq[r] : 0.0;
+            a = fma(xp[u][i], xp[u][i], a);
+            b = fma(xq[u][i], xq[u][i], b);
+            c = fma(xp[u][i], xq[u][i], c);
+          }
+          // three sums with 7 exchanges: lanes split the values after the first butterfly step
+          {
+            const bool h16 = lane & 16, h8 = lane & 8;
+            // step 1 (xor 16): low half keeps (a, b), high half keeps (c, 0)
+            const double s0 = h16 ? a : c, s1 = h16 ? b : 0.0;
+            const double k0 = h16 ? c : a, k1 = h16 ? 0.0 : b;
+            const double r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+            const double r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+            // step 2 (xor 8): keep one value
+            double v = (h8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, h8 ? r0 : r1, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            // lanes 0-7: a, 8-15: b, 16-23: c
+            if (lane == 0) s_a[pr] = v;
+            if (lane == 8) s_b[pr] = v;
+            if (lane == 16) s_c[pr] = v;
+          }
         }
-        a = warp_sum(a);
-        b = warp_sum(b);
-        c = warp_sum(c);
+      }
+      __syncthreads();
+      if (tid < npairs) {
+        const double a = s_a[tid], b = s_b[tid], c = s_c[tid];
+        double cs = 1.0, sn = 0.0;
         if (fabs(c) > tol * sqrt(a * b) && a > 0.0 && b > 0.0) {
           rotated = 1;
           const double zeta = (b - a) / (2.0 * c);
           const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t);
-          const double sn = cs * t;
+          cs = 1.0 / sqrt(1.0 + t * t);
+          sn = cs * t;
+        }
+        s_cs[tid] = cs;
+        s_sn[tid] = sn;
+      }
+      __syncthreads();
 #pragma unroll
-          for (int i = 0; i < NPL; ++i) {
-            const int r = lane + 32 * i;
-            if (r < n) {
-              gp[r] = cs * xp[i] - sn * xq[i];
-              gq[r] = sn * xp[i] + cs * xq[i];
+      for (int u = 0; u < PPW; ++u) {
+        const int pr = warp + u * nwarp;
+        if (pr < npairs) {
+          const double cs = s_cs[pr], sn = s_sn[pr];
+          if (sn != 0.0) {
+            double* gp = G + (size_t)pp[u] * ldg;
+            double* gq = G + (size_t)qq[u] * ldg;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+              const int r = lane + 32 * i;
+              if (r < n) {
+                gp[r] = cs * xp[u][i] - sn * xq[u][i];
+                gq[r] = sn * xp[u][i] + cs * xq[u][i];
+              }
             }
           }
         }
@@ -172,25 +221,25 @@ int jacobi_syev_batched(int n, const double* A, int lda, long long strideA, doub
   int warps = npairs < 32 ? npairs : 32;
   if (warps < 1) warps = 1;
   const int threads = warps * 32;
-#define GSCF_JACOBI_LAUNCH(NPL)                                                                  \
+#define GSCF_JACOBI_LAUNCH(NPL, PPW)                                                                \
   do {                                                                                           \
     static bool cfg = false;                                                                     \
     if (!cfg) {                                                                                  \
-      GSCF_CUDA_TRY(cudaFuncSetAttribute(jacobi_onesided_kernel<NPL>,                            \
+      GSCF_CUDA_TRY(cudaFuncSetAttribute(jacobi_onesided_kernel<NPL, PPW>,                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                          (int)jacobi_smem_bytes(32 * NPL > kJacobiMaxN          \
                                                                     ? kJacobiMaxN               \
                                                                     : 32 * NPL)));              \
       cfg = true;                                                                                \
     }                                                                                            \
-    jacobi_onesided_kernel<NPL><<<batch, threads, smem, st>>>(A, lda, strideA, w, stride_w, Z,   \
+    jacobi_onesided_kernel<NPL, PPW><<<batch, threads, smem, st>>>(A, lda, strideA, w, stride_w, Z, \
                                                               ldz, strideZ, n, batch_map,       \
                                                               info_dev);                        \
   } while (0)
-  if (n <= 32) GSCF_JACOBI_LAUNCH(1);
-  else if (n <= 64) GSCF_JACOBI_LAUNCH(2);
-  else if (n <= 128) GSCF_JACOBI_LAUNCH(4);
-  else GSCF_JACOBI_LAUNCH(5);
+  if (n <= 32) GSCF_JACOBI_LAUNCH(1, 1);
+  else if (n <= 64) GSCF_JACOBI_LAUNCH(2, 1);
+  else if (n <= 128) GSCF_JACOBI_LAUNCH(4, 2);
+  else GSCF_JACOBI_LAUNCH(5, 3);
 #undef GSCF_JACOBI_LAUNCH
   count_launch();
   GSCF_CHECK_LAUNCH();

@@ -107,6 +107,90 @@ __global__ void dc_leaf_scatter_kernel(StedcWs ws, double* __restrict__ Z0, int 
   }
 }
 
+// Leaf solver: implicit-shift QL iteration (the EISPACK tql2 / LAPACK dsteqr recurrence) on the m <= 32 tridiagonal
+// leaf, one WARP per leaf.  The scalar recurrence is uniform across the warp; lane k owns row k of the eigenvector
+// matrix, so a plane rotation of two columns is one shared-memory read-modify-write per lane.  Writes the leaf's
+// eigenvectors into the block diagonal of Z0 and its eigenvalues (any order) into lam[0].
+constexpr int kLeafWarps = 8;
+__global__ void __launch_bounds__(kLeafWarps * 32)
+dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws, double* __restrict__ Z0, int ldz,
+                    long long sZ, int nbatch, const int* __restrict__ map) {
+  extern __shared__ __align__(16) double lsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gl = (long long)blockIdx.x * kLeafWarps + warp;  // leaves of all matrices, flattened
+  if (gl >= (long long)ws.nleaf * nbatch) return;
+  const int zb = (int)(gl / ws.nleaf), leaf = (int)(gl - (long long)zb * ws.nleaf);
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n, L = ws.L;
+  const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
+  double* Zs = lsm + (size_t)warp * (kLeaf * kLeaf + 2 * kLeaf);  // Zs[col * 32 + row]
+  double* sd = Zs + kLeaf * kLeaf;
+  double* se = sd + kLeaf;
+  const double* dm = ws.dmod + q * n + lo;
+  const double* eq = e + q * dstride + lo;
+  for (int c = 0; c < m; ++c) Zs[c * kLeaf + lane] = (c == lane) ? 1.0 : 0.0;
+  if (lane < m) {
+    sd[lane] = dm[lane];
+    se[lane] = lane < m - 1 ? eq[lane] : 0.0;
+  }
+  __syncwarp();
+  const double eps = 2.220446049250313e-16;
+  for (int l = 0; l < m; ++l) {
+    for (int iter = 0; iter < 60; ++iter) {
+      int mm = l;
+      for (; mm < m - 1; ++mm) {
+        const double dd = fabs(sd[mm]) + fabs(sd[mm + 1]);
+        if (fabs(se[mm]) <= eps * dd) break;
+      }
+      if (mm == l) break;
+      const double dl = sd[l], el = se[l];
+      double g = (sd[l + 1] - dl) / (2.0 * el);
+      double r = hypot(g, 1.0);
+      g = sd[mm] - dl + el / (g + copysign(r, g));
+      __syncwarp();
+      double sn = 1.0, cs = 1.0, p = 0.0;
+      int i = mm - 1;
+      bool underflow = false;
+      for (; i >= l; --i) {
+        const double ei = se[i], di1 = sd[i + 1], di = sd[i];
+        __syncwarp();  // every lane has read this step's entries before lane 0 overwrites them
+        const double f = sn * ei, b = cs * ei;
+        r = sqrt(fma(f, f, g * g));  // entries are bounded by the leaf's norm; an underflow to 0 takes the exit below
+        if (lane == 0) se[i + 1] = r;
+        if (r == 0.0) {
+          if (lane == 0) { sd[i + 1] = di1 - p; se[mm] = 0.0; }
+          underflow = true;
+          break;
+        }
+        const double rinv = 1.0 / r;
+        sn = f * rinv;
+        cs = g * rinv;
+        g = di1 - p;
+        r = (di - g) * sn + 2.0 * cs * b;
+        p = sn * r;
+        if (lane == 0) sd[i + 1] = g + p;
+        g = cs * r - b;
+        if (lane < m) {
+          const double z1 = Zs[(i + 1) * kLeaf + lane], z0 = Zs[i * kLeaf + lane];
+          Zs[(i + 1) * kLeaf + lane] = sn * z0 + cs * z1;
+          Zs[i * kLeaf + lane] = cs * z0 - sn * z1;
+        }
+      }
+      __syncwarp();
+      if (!underflow) {
+        if (lane == 0) { sd[l] = dl - p; se[l] = g; se[mm] = 0.0; }
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  double* Zq = Z0 + q * sZ;
+  double* lam = ws.lam[0] + q * n;
+  for (int c = 0; c < m; ++c)
+    if (lane < m) Zq[(size_t)(lo + c) * ldz + lo + lane] = Zs[c * kLeaf + lane];
+  if (lane < m) lam[lo + lane] = sd[lane];
+}
+
 __global__ void zero_matrix_kernel(double* __restrict__ Z, int ldz, long long sZ, int n,
                                    const int* __restrict__ map) {
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
@@ -482,7 +566,12 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
   };
   ws.n = n; ws.ld = padded_ld(n); ws.cap = cap;
   int L = 0;
-  while (ceil_div(n, 1 << L) > kLeaf) ++L;
+  // leaves: 32 for batches (throughput: fewer merge levels), 16 for a few large matrices (latency: the QL iteration of
+  // a leaf is a serial chain of ~m^2 rotations; measured n = 1024: 5.90 ms with 32, 5.64 ms with 16)
+  static int leaf_env = -1;
+  if (leaf_env < 0) { const char* le = getenv("GSCF_B200_DC_LEAF"); leaf_env = le ? std::max(4, std::min(kLeaf, atoi(le))) : 0; }
+  const int leaf_target = leaf_env > 0 ? leaf_env : (cap <= 8 ? 16 : kLeaf);
+  while (ceil_div(n, 1 << L) > leaf_target) ++L;
   ws.L = L; ws.nleaf = 1 << L;
   ws.lmax = ceil_div(n, 1 << L);
   const size_t cn = (size_t)cap * n;
@@ -513,7 +602,7 @@ int stedc_batched(int n, const double* d, const double* e, long long dstride, do
                   double* Z, int ldz, long long strideZ, const StedcWs& ws, int batch, const int* map,
                   int* info_dev, cudaStream_t st) {
   if (batch <= 0) return GSCF_B200_OK;
-  const int L = ws.L, lm = ws.lmax;
+  const int L = ws.L;
   const int gx = std::max(1, std::min(148 * 4 / std::max(1, batch), ceil_div(n * n, 256 * 8)));
   // buffers: X_0 (leaf eigenvectors) -> level 1 -> ... -> X_L -> sorted into Z
   // X_L must be the workspace buffer, so X_0 = Zb for even L and Z for odd L.
@@ -524,13 +613,17 @@ int stedc_batched(int n, const double* d, const double* e, long long dstride, do
   int cur = first;
   // ---- leaves -----------------------------------------------------------------------------------------
   dc_split_kernel<<<dim3(std::max(1, ceil_div(n, 256)), batch), 256, 0, st>>>(d, e, dstride, ws, map);
-  dc_leaf_build_kernel<<<dim3(ws.nleaf, batch), 256, 0, st>>>(e, dstride, ws, map);
-  count_launch(2);
+  count_launch(1);
   GSCF_CHECK_LAUNCH();
-  GSCF_TRY(jacobi_syev_batched(lm, ws.leafA, lm, (long long)lm * lm, ws.leafW, lm, ws.leafZ, lm, (long long)lm * lm,
-                               ws.nleaf * batch, nullptr, nullptr, st));
+  static bool leaf_cfg = false;
+  const size_t leaf_smem = (size_t)kLeafWarps * (kLeaf * kLeaf + 2 * kLeaf) * sizeof(double);
+  if (!leaf_cfg) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_leaf_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem));
+    leaf_cfg = true;
+  }
   zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[cur], bufld[cur], bufs[cur], n, map);
-  dc_leaf_scatter_kernel<<<dim3(ws.nleaf, batch), 256, 0, st>>>(ws, bufp[cur], bufld[cur], bufs[cur], map);
+  dc_leaf_tql2_kernel<<<(unsigned)ceil_div_ll((long long)ws.nleaf * batch, kLeafWarps), kLeafWarps * 32, leaf_smem, st>>>(
+      e, dstride, ws, bufp[cur], bufld[cur], bufs[cur], batch, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   int lev = 0;

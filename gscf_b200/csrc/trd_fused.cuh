@@ -27,6 +27,7 @@
 // timeout + global abort flag); an aborted reduction poisons d[0] with NaN so that the divide &
 // conquer stage flags the matrix as failed.
 #pragma once
+#include <cooperative_groups.h>
 
 namespace gscfb {
 namespace {
@@ -41,6 +42,8 @@ struct TfArgs {
   double *d, *e, *tau;   // [cap][n]
   unsigned* abort_flag;  // one word, zero on entry
   const int* map; int mat0; int n;
+  int cluster;           // launched as one thread-block cluster per matrix: the exchange uses the hardware cluster barrier
+  int smax;              // stride of the per-warp partial sums: >= owned columns per CTA, multiple of 8
 };
 
 __device__ __forceinline__ double tf_ld(const double* p) {
@@ -75,13 +78,17 @@ __device__ __forceinline__ double tf_block_sum(double v, double* red) {
 }
 
 inline long long tf_x_doubles(int n) { return 4LL * ((n + 1) & ~1); }
+inline int tf_smax(int n, int G) { return round_up(ceil_div(n, G), 8); }
 inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
   const int np = round_up(n, 2);
   const int S = ceil_div(n, G);
-  return ((size_t)3 * np + 32 * TF_MAXS + 32 + 32 + 8 + (smem_a ? (size_t)S * np : 0)) * sizeof(double);
+  // v (x2), w, [solo: y, raw], per-warp partials, reduction scratch, owned columns
+  return ((size_t)(G == 1 ? 5 : 3) * np + 32 * tf_smax(n, G) + 32 + 32 + 8 + (smem_a ? (size_t)S * np : 0)) * sizeof(double);
 }
 
-template <int KMAX, bool SMEM_A, int T>
+// SOLO: one CTA owns the whole matrix (n <= ~150, batches of small problems): the exchange is two shared-memory
+// vectors, no counter, no global round trip.
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false>
 __global__ void __launch_bounds__(T, 1)
 trd_fused_kernel(const TfArgs a) {
   const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,8 +103,11 @@ trd_fused_kernel(const TfArgs a) {
   double* sv0 = tf_smem;
   double* sv1 = sv0 + np;
   double* sw = sv1 + np;
-  double* spart = sw + np;             // [32][TF_MAXS] per-warp partial y
-  double* sred1 = spart + 32 * TF_MAXS;
+  double* sy = sw + np;                // SOLO: y and the raw column
+  double* sraw = sy + (SOLO ? np : 0);
+  double* spart = sraw + (SOLO ? np : 0);  // [32][smax] per-warp partial y
+  const int smax = a.smax;
+  double* sred1 = spart + 32 * smax;
   double* sred2 = sred1 + 32;
   double* sbc = sred2 + 32;            // 0: y[first]  1: a'[first+1]
   double* sAc = sbc + 8;               // SMEM_A: owned columns, slot s at sAc + s*np
@@ -145,71 +155,143 @@ trd_fused_kernel(const TfArgs a) {
       double* Xy = X + (size_t)(j & 1) * 2 * np;
       double* Xr = Xy + np;
       const bool pub_raw = (g + s0 * G == first);  // I own column j+1: its updated values are the raw column
-      for (int sg = s0; sg < S; sg += TF_CG) {
-        double acc[TF_CG], wc[TF_CG], vc[TF_CG];
-#pragma unroll
-        for (int u = 0; u < TF_CG; ++u) {
-          const int slot = sg + u;
-          const int c = g + slot * G;
-          acc[u] = 0.0;
-          wc[u] = slot < S ? sw[c] : 0.0;   // w_{j-1}(c)
-          vc[u] = slot < S ? svn[c] : 0.0;  // v_{j-1}(c): after the swap svn holds the previous reflector
-        }
-        for (int p = tid; p < npairs; p += T) {
-          const int r = r_lo + 2 * p;
-          const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
-          const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
-          const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
-          double2 av[TF_CG];
-#pragma unroll
+      if (SOLO) {
+        // few rows (n <= ~150): one WARP per group of 8 columns, lanes over the row pairs - the block-wide mapping
+        // below would leave three quarters of the threads without a row
+        for (int sg = s0 + warp * TF_CG; sg < S; sg += NW * TF_CG) {
+          double acc[TF_CG], wc[TF_CG], vc[TF_CG];
+  #pragma unroll
           for (int u = 0; u < TF_CG; ++u) {
             const int slot = sg + u;
-            if (slot < S) {
-              const double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
-              av[u] = *reinterpret_cast<const double2*>(col + r);
-            }
+            const int c = g + slot * G;
+            acc[u] = 0.0;
+            wc[u] = slot < S ? sw[c] : 0.0;   // w_{j-1}(c)
+            vc[u] = slot < S ? svn[c] : 0.0;  // v_{j-1}(c): after the swap svn holds the previous reflector
           }
-          const bool odd_tail = !SMEM_A && (r + 1 >= n);  // pad row of an odd-order matrix in global memory
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) {
-            const int slot = sg + u;
-            if (slot < S) {
-              double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
-              double2 x = av[u];
-              x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
-              x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
-              if (odd_tail) {
-                x.y = 0.0;
-                col[r] = x.x;
-              } else {
-                *reinterpret_cast<double2*>(col + r) = x;
+          for (int p = lane; p < npairs; p += 32) {
+            const int r = r_lo + 2 * p;
+            const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
+            const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
+            const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
+            double2 av[TF_CG];
+  #pragma unroll
+            for (int u = 0; u < TF_CG; ++u) {
+              const int slot = sg + u;
+              if (slot < S) {
+                const double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+                av[u] = *reinterpret_cast<const double2*>(col + r);
               }
-              if (pub_raw && slot == s0) *reinterpret_cast<double2*>(Xr + r) = x;
-              acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
+            }
+            const bool odd_tail = !SMEM_A && (r + 1 >= n);  // pad row of an odd-order matrix in global memory
+  #pragma unroll
+            for (int u = 0; u < TF_CG; ++u) {
+              const int slot = sg + u;
+              if (slot < S) {
+                double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+                double2 x = av[u];
+                x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+                x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+                if (odd_tail) {
+                  x.y = 0.0;
+                  col[r] = x.x;
+                } else {
+                  *reinterpret_cast<double2*>(col + r) = x;
+                }
+                if (pub_raw && slot == s0) *reinterpret_cast<double2*>((SOLO ? sraw : Xr) + r) = x;
+                acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
+              }
             }
           }
+          {
+            // 8 sums over the warp with 7 exchanges instead of 40: every butterfly step halves the number of values a
+            // lane is responsible for (SHFL issues at one warp per clock per SM - 80 of them per warp dominated the sweep)
+            static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            double a4[4], a2[2];
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+  #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+            if ((lane & 3) == 0 && sg + u < S) sy[sg + u] = a1;  // the warp owns these columns: complete sums
+          }
         }
-        {
-          // 8 sums over the warp with 7 exchanges instead of 40: every butterfly step halves the number of values a
-          // lane is responsible for (SHFL issues at one warp per clock per SM - 80 of them per warp dominated the sweep)
-          static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
-          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-          double a4[4], a2[2];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
-            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      } else {
+        for (int sg = s0; sg < S; sg += TF_CG) {
+          double acc[TF_CG], wc[TF_CG], vc[TF_CG];
+  #pragma unroll
+          for (int u = 0; u < TF_CG; ++u) {
+            const int slot = sg + u;
+            const int c = g + slot * G;
+            acc[u] = 0.0;
+            wc[u] = slot < S ? sw[c] : 0.0;   // w_{j-1}(c)
+            vc[u] = slot < S ? svn[c] : 0.0;  // v_{j-1}(c): after the swap svn holds the previous reflector
           }
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
-            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          for (int p = tid; p < npairs; p += T) {
+            const int r = r_lo + 2 * p;
+            const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
+            const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
+            const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
+            double2 av[TF_CG];
+  #pragma unroll
+            for (int u = 0; u < TF_CG; ++u) {
+              const int slot = sg + u;
+              if (slot < S) {
+                const double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+                av[u] = *reinterpret_cast<const double2*>(col + r);
+              }
+            }
+            const bool odd_tail = !SMEM_A && (r + 1 >= n);  // pad row of an odd-order matrix in global memory
+  #pragma unroll
+            for (int u = 0; u < TF_CG; ++u) {
+              const int slot = sg + u;
+              if (slot < S) {
+                double* col = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)(g + slot * G) * lda;
+                double2 x = av[u];
+                x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+                x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+                if (odd_tail) {
+                  x.y = 0.0;
+                  col[r] = x.x;
+                } else {
+                  *reinterpret_cast<double2*>(col + r) = x;
+                }
+                if (pub_raw && slot == s0) *reinterpret_cast<double2*>((SOLO ? sraw : Xr) + r) = x;
+                acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
+              }
+            }
           }
-          double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-          const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-          if ((lane & 3) == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = a1;
+          {
+            // 8 sums over the warp with 7 exchanges instead of 40: every butterfly step halves the number of values a
+            // lane is responsible for (SHFL issues at one warp per clock per SM - 80 of them per warp dominated the sweep)
+            static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            double a4[4], a2[2];
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+  #pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+            if ((lane & 3) == 0 && sg + u < S) spart[warp * smax + sg + u] = a1;
+          }
         }
       }
 #ifdef GSCF_TF_DEBUG_TIMING
@@ -218,39 +300,46 @@ trd_fused_kernel(const TfArgs a) {
       TF_TICK(0);
       __syncthreads();
       TF_TICK(1);
-      if (tid < S - s0) {
-        const int slot = s0 + tid;
-        double y = 0.0;
+      if (!SOLO) {
+        for (int slot = s0 + tid; slot < S; slot += T) {
+          double y = 0.0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) y += spart[w * TF_MAXS + slot];
-        Xy[g + slot * G] = y;
+          for (int w = 0; w < NW; ++w) y += spart[w * smax + slot];
+          Xy[g + slot * G] = y;
+        }
       }
       // ================= exchange: arrive, wait for the other CTAs, load y and the raw column =================
       TF_TICK(2);
       __syncthreads();  // the y stores above and the raw stores of the sweep are ordered before the fence below
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        const unsigned target = (unsigned)G * (unsigned)(j + 1);
-        if (*reinterpret_cast<volatile unsigned*>(a.abort_flag) == 0u) {
-          const long long t0 = clock64();
-          int spins = 0;
-          while (tf_ld_acquire(ctr) < target) {
-            if ((++spins & 255) == 0 &&
-                (clock64() - t0 > 2000000000LL || *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)) {
-              atomicExch(a.abort_flag, 1u);
-              break;
+      if (!SOLO && a.cluster) {
+        // barrier.cluster.arrive.release / wait.acquire: the y and raw stores of every CTA of the cluster are visible
+        // to all of them afterwards; no L2 atomic, no polling
+        cooperative_groups::this_cluster().sync();
+      } else if (!SOLO) {
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(ctr, 1u);
+          const unsigned target = (unsigned)G * (unsigned)(j + 1);
+          if (*reinterpret_cast<volatile unsigned*>(a.abort_flag) == 0u) {
+            const long long t0 = clock64();
+            int spins = 0;
+            while (tf_ld_acquire(ctr) < target) {
+              if ((++spins & 255) == 0 &&
+                  (clock64() - t0 > 2000000000LL || *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)) {
+                atomicExch(a.abort_flag, 1u);
+                break;
+              }
             }
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int r = tid + k * T;
         const bool need = r >= first && r < n;
-        yv[k] = need ? tf_ld(Xy + r) : 0.0;
-        rv[k] = need ? tf_ld(Xr + r) : 0.0;
+        yv[k] = need ? (SOLO ? sy[r] : tf_ld(Xy + r)) : 0.0;
+        rv[k] = need ? (SOLO ? sraw[r] : tf_ld(Xr + r)) : 0.0;
       }
     }
     TF_TICK(3);
@@ -322,7 +411,7 @@ trd_fused_kernel(const TfArgs a) {
     printf("\n");
   }
 #endif
-  if (g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
+  if (!SOLO && g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
     (a.d + q * n)[0] = __longlong_as_double(0x7ff8000000000000LL);
 }
 

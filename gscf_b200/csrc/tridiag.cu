@@ -537,10 +537,10 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 }
 
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
-template <int KMAX, bool SMEM_A, int T>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
   static bool configured = false;
-  auto kern = trd_fused_kernel<KMAX, SMEM_A, T>;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO>;
   if (!configured) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -560,7 +560,7 @@ int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaSt
     attr[0].val.cooperative = 1;
   }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = SOLO ? 0 : 1;  // a single CTA per matrix waits for nobody: ordinary launch, any batch size
   GSCF_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
   count_launch();
   return GSCF_B200_OK;
@@ -644,7 +644,7 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   if (!enabled || n < 3 || (lda & 1) || n > 8192) return -1;
   const int np = round_up(n, 2);
   constexpr size_t kSmemMax = 220 * 1024;
-  const int g_slots = ceil_div(n, TF_MAXS);                       // S <= TF_MAXS
+  const int g_slots = 1;
   int g_smem = 0;                                                 // fewest CTAs with the columns in shared memory
   if (!force_global && n <= 2048) {
     for (int G = g_slots; G <= sms; ++G)
@@ -653,7 +653,12 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   // group size and launch mode
   int G = 0;
   bool cluster = false, smem_a = false;
-  if (g_smem > 0 && batch * g_smem > sms && g_smem <= 16) {
+  static int solo_ok = -1;
+  if (solo_ok < 0) { const char* se = getenv("GSCF_B200_TF_SOLO"); solo_ok = (se && se[0] == '0') ? 0 : 1; }
+  const bool solo = solo_ok && !force_global && tf_smem_bytes(n, 1, true) <= kSmemMax;
+  if (solo) {
+    G = 1; smem_a = true;
+  } else if (g_smem > 0 && batch * g_smem > sms && g_smem <= 16) {
     // more matrices than fit side by side: one thread-block cluster per matrix, scheduled by the hardware
     G = g_smem <= 8 ? 8 : 16;
     cluster = true; smem_a = true;
@@ -673,6 +678,7 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
+    if (solo) return tf_launch<1, true, 256, true>(a, G, cnt, false, smem, st);
     if (smem_a) {
       if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
@@ -685,7 +691,8 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   };
   static int blocked = -1;
   if (blocked < 0) { const char* be = getenv("GSCF_B200_TF_BLOCKED"); blocked = (be && be[0] == '0') ? 0 : 1; }
-  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below();
+  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below() &&
+                           ceil_div(n, G) <= TF_MAXS;
   if (cluster) {
     int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
                     : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
@@ -693,10 +700,15 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   }
   TfArgs a;
   a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = ws.d; a.e = ws.e; a.tau = ws.tau;
-  a.abort_flag = ws.bar + 2 * ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n;
+  a.abort_flag = ws.bar + 2 * ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n; a.smax = tf_smax(n, G);
+  {
+    static int cb = -1;
+    if (cb < 0) { const char* ce = getenv("GSCF_B200_TF_CLUSTER_BARRIER"); cb = (ce && ce[0] == '0') ? 0 : 1; }
+    a.cluster = (cluster && cb) ? 1 : 0;
+  }
   GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)2 * ws.cap + 1) * sizeof(unsigned), st));
   phase_mark(PH_SYMV_SAMPLE, true, st);
-  const int per_launch = cluster ? 32768 : std::max(1, sms / G);
+  const int per_launch = (cluster || solo) ? 32768 : std::max(1, sms / G);
   for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
     a.mat0 = mat0;
     const int cnt = std::min(per_launch, batch - mat0);

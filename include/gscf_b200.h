@@ -52,7 +52,7 @@ typedef enum gscf_b200_status {
 typedef enum gscf_b200_memloc { GSCF_B200_HOST = 0, GSCF_B200_DEVICE = 1 } gscf_b200_memloc;
 
 typedef enum gscf_b200_eig_method {
-  GSCF_B200_EIG_AUTO = 0,     /* Jacobi for n <= 128, tridiagonal + divide&conquer above */
+  GSCF_B200_EIG_AUTO = 0,     /* Jacobi for n <= 64, tridiagonal + divide&conquer above */
   GSCF_B200_EIG_JACOBI = 1,   /* batched cyclic Jacobi in shared memory (n <= 128) */
   GSCF_B200_EIG_TRIDIAG_DC = 2/* Householder tridiagonalisation + D&C + back-transformation */
 } gscf_b200_eig_method;

@@ -32,3 +32,4 @@ if __name__ == "__main__":
     if "c5full" in which: run(512, 64, 32, 4, P=256, n_beta=60, reps=1)
     if "c5" in which: run(512, 64, 32, 4, P=16, n_beta=60)
     if "mid" in which: run(512, 64, 32, 8)
+    if "c4dc" in which: run(128, 16, 8, 4, P=4096, eig=2, reps=2)
