@@ -273,3 +273,26 @@ def test_syev_tridiag_dc_fock_like(env):
     A = X @ F[0] @ X
     A = 0.5 * (A + A.T)
     _syev_check(torch, L, L.EIG_TRIDIAG_DC, [A, X @ p.H @ X], 384)
+
+
+@pytest.mark.parametrize("n,batch,envs", [
+    (333, 2, {"GSCF_B200_TF_GLOBAL": "1"}),                                        # trailing matrix in global memory
+    (600, 1, {"GSCF_B200_TF_GLOBAL": "1", "GSCF_B200_TF_UNBLOCKED_BELOW": "64"}),   # blocked (deferred updates)
+    (257, 3, {"GSCF_B200_TF_GLOBAL": "1", "GSCF_B200_TF_UNBLOCKED_BELOW": "100"}),  # blocked, odd order, switch-over
+    (128, 40, {"GSCF_B200_TF_SOLO": "0"}),                                          # one cluster per matrix
+    (512, 12, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # clusters with the L2 counter exchange
+    (130, 5, {}),                                                                   # one CTA per matrix (SOLO)
+    (1024, 2, {"GSCF_B200_TF_FUSED": "0"}),                                         # previous panel kernels still work
+])
+def test_syev_fused_variants(env, n, batch, envs):
+    """Every storage / exchange variant of the fused tridiagonalisation (trd_fused.cuh, trd_fused_blk.cuh)."""
+    import os
+    import subprocess
+    import sys
+
+    child_env = dict(os.environ)
+    child_env.update(envs)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "syev_variant_main.py"), str(n), str(batch)],
+                       cwd=root, env=child_env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
