@@ -21,7 +21,7 @@ namespace gscfb {
 namespace {
 
 constexpr int NB = 32;    // tridiagonalisation panel width
-constexpr int NBQ = 64;   // back-transformation block width
+constexpr int NBQ = 128;  // back-transformation block width (64: 20.0 ms, 128: see DESIGN.md section 5, n = 4096)
 constexpr int RB = 128;   // rows per CTA in the vector kernels
 constexpr int TS = 128;   // symv tile edge
 
@@ -40,17 +40,13 @@ struct TrdWs {
   double* VPW;          // [cap][2][32][np] pending reflector panels of the blocked fused kernel
   double* PQ;           // [cap][2][256][64] partial dots of the blocked fused kernel
   int npart;            // entries per matrix in pnorm / pdot
-  double* Vc;           // [cap][ld*NBQ]
   double* Vf;           // [cap][ld*n]  all reflectors, unit lower trapezoidal, zeros above
   double* Wf;           // [cap][ld*n]  V_b T_b per block of NBQ reflectors
   double* Gall;         // [cap][nbq][NBQ*NBQ]  V_b^T V_b
   double* Tall;         // [cap][nbq][NBQ*NBQ]  T_b
   GemmDesc* bdesc;      // [cap][nbq] descriptors of the per-block set-up GEMMs
   int nbq;              // blocks of NBQ reflectors
-  double* Tf;           // [cap][NBQ*NBQ]
-  double* Gm;           // [cap][NBQ*NBQ]
   double* Yw;           // [cap][NBQ*n]
-  double* Y2;           // [cap][NBQ*n]
   int n, ld, nrb, ncb, cap;
 };
 inline int ws_cap_hint(const TrdWs& ws) { return ws.cap; }
@@ -275,44 +271,20 @@ trd_finalize_w(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, i
 }
 
 // ---- back-transformation helpers ---------------------------------------------------------------------
-// Vc (rows j0+1.., pw columns): unit lower trapezoidal copy of the reflectors of columns j0..j0+pw-1
-__global__ void extract_v_kernel(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int j0, int pw,
-                                 const int* __restrict__ map) {
-  const long long q = map ? map[blockIdx.z] : blockIdx.z;
-  const int n = ws.n;
-  const double* A = Ab + q * sA;
-  double* Vc = ws.Vc + q * (long long)ws.ld * NBQ;
-  const int j = blockIdx.y;
-  const int m = n - j0 - 1;  // rows of Vc
-  for (int rr = blockIdx.x * blockDim.x + threadIdx.x; rr < m; rr += gridDim.x * blockDim.x) {
-    const int r = j0 + 1 + rr;          // absolute row
-    const int diag = j0 + j + 1;        // unit position of column j
-    double v = 0.0;
-    if (r == diag) v = 1.0;
-    else if (r > diag) v = A[(size_t)(j0 + j) * lda + r];
-    Vc[(size_t)j * ws.ld + rr] = v;
-  }
-  (void)pw;
-}
-
 // T (pw x pw upper triangular, the dlarft factor) from G = V^T V and tau through T^-1 = diag(1/tau) + striu(G):
 // column c of T solves the triangular system by back substitution,
 //   T(c,c) = tau_c,   T(r,c) = -tau_r sum_{k=r+1..c} G(r,k) T(k,c),   r = c-1 .. 0
 // (tau_r = 0, i.e. H_r = I, gives a zero row and column, as dlarft does).  The columns are independent: one quad
 // of threads per column, no block-wide barrier inside the recurrence.
-__global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, const int* __restrict__ map) {
+__global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __restrict__ map) {
   extern __shared__ double sm[];
   constexpr int LDT = NBQ + 1;
-  double* Gt = sm;                 // Gt[r*LDT + k] = G(r,k)
-  double* X = sm + NBQ * LDT;      // X[c*LDT + k] = T(k,c)
+  double* X = sm;                  // X[c*LDT + k] = T(k,c)
   __shared__ double stau[NBQ];
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
   const int b = blockIdx.x, j0 = b * NBQ, pw = min(NBQ, ws.n - 1 - j0);
-  const double* Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw
-  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
-    const int k = idx / pw, r = idx - k * pw;
-    Gt[r * LDT + k] = Gg[idx];
-  }
+  // G is symmetric: row r is read as column r (contiguous in k), straight from L2 / L1
+  const double* __restrict__ Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw
   for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = (ws.tau + q * ws.n + j0)[idx];
   __syncthreads();
   const int c = threadIdx.x >> 2, part = threadIdx.x & 3;
@@ -322,9 +294,9 @@ __global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, const int* __restr
     if (part == 0) x[c] = stau[c];
     __syncwarp(qmask);
     for (int r = c - 1; r >= 0; --r) {
-      const double* g = Gt + r * LDT;
+      const double* g = Gg + (size_t)r * pw;
       double s = 0.0;
-      for (int k = r + 1 + part; k <= c; k += 4) s = fma(g[k], x[k], s);
+      for (int k = r + 1 + part; k <= c; k += 4) s = fma(__ldg(g + k), x[k], s);
       s += __shfl_xor_sync(qmask, s, 1);
       s += __shfl_xor_sync(qmask, s, 2);
       if (part == 0) x[r] = -stau[r] * s;
@@ -337,51 +309,6 @@ __global__ void __launch_bounds__(256) larft_kernel(TrdWs ws, const int* __restr
     const int cc = idx / pw, r = idx - cc * pw;
     Tg[idx] = r <= cc ? X[cc * LDT + r] : 0.0;
   }
-}
-
-// Y2 = T Y without forming T: T^-1 = diag(1/tau) + striu(V^T V) (upper triangular), so the rows of
-// Y2 follow by back substitution  Y2[j] = tau_j (Y[j] - sum_{k>j} G(j,k) Y2[k]),  j = pw-1 .. 0.
-// One thread per right-hand side (a column of Z); G and tau in shared memory.  tau_j = 0 (H_j = I)
-// gives Y2[j] = 0, consistent with T(j,:) = T(:,j) = 0.
-template <int PW>
-__global__ void __launch_bounds__(128)
-wy_trsm_kernel(TrdWs ws, int j0, int pw, int ncols, const int* __restrict__ map) {
-  // G^T in shared memory (row j of G contiguous), the solution vectors of the CTA's 128 right-hand
-  // sides in shared memory as x[j][thread]: runtime loops (a fully unrolled register version was
-  // instruction-cache bound: 91 us per launch)
-  extern __shared__ double sm_trsm[];
-  double* sGt = sm_trsm;                   // [PW][PW+1]: sGt[j*(PW+1) + k] = G(j,k)
-  double* sx = sGt + PW * (PW + 1);        // [PW][128]
-  __shared__ double stau[PW];
-  const long long q = map ? map[blockIdx.y] : blockIdx.y;
-  const double* Gg = ws.Gm + q * NBQ * NBQ;  // column-major, ld = pw
-  const double* tau = ws.tau + q * ws.n + j0;
-  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
-    const int k = idx / pw, jj = idx - k * pw;  // G(jj, k)
-    sGt[jj * (PW + 1) + k] = Gg[idx];
-  }
-  for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = tau[idx];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool act = c < ncols;
-  const double* y = ws.Yw + q * (long long)NBQ * ws.n + (size_t)(act ? c : 0) * NBQ;
-  double* y2 = ws.Y2 + q * (long long)NBQ * ws.n + (size_t)(act ? c : 0) * NBQ;
-  for (int jj = 0; jj < pw; ++jj) sx[jj * 128 + threadIdx.x] = act ? y[jj] : 0.0;
-  __syncthreads();
-  for (int jj = pw - 1; jj >= 0; --jj) {
-    const double* grow = sGt + jj * (PW + 1);
-    double s0 = sx[jj * 128 + threadIdx.x], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = jj + 1;
-    for (; k + 4 <= pw; k += 4) {
-      s0 = fma(-grow[k], sx[k * 128 + threadIdx.x], s0);
-      s1 = fma(-grow[k + 1], sx[(k + 1) * 128 + threadIdx.x], s1);
-      s2 = fma(-grow[k + 2], sx[(k + 2) * 128 + threadIdx.x], s2);
-      s3 = fma(-grow[k + 3], sx[(k + 3) * 128 + threadIdx.x], s3);
-    }
-    for (; k < pw; ++k) s0 = fma(-grow[k], sx[k * 128 + threadIdx.x], s0);
-    sx[jj * 128 + threadIdx.x] = stau[jj] * ((s0 + s1) + (s2 + s3));
-  }
-  if (act)
-    for (int jj = 0; jj < pw; ++jj) y2[jj] = sx[jj * 128 + threadIdx.x];
 }
 
 __global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __restrict__ eout, const int* map) {
@@ -431,17 +358,13 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
-  ws.Vc = cv.take<double>((size_t)cap * ld * NBQ);
   ws.nbq = std::max(1, ceil_div(n - 1, NBQ));
   ws.Vf = cv.take<double>((size_t)cap * ld * n);
   ws.Wf = cv.take<double>((size_t)cap * ld * n);
   ws.Gall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
   ws.Tall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
   ws.bdesc = cv.take<GemmDesc>((size_t)cap * ws.nbq);
-  ws.Tf = cv.take<double>((size_t)cap * NBQ * NBQ);
-  ws.Gm = cv.take<double>((size_t)cap * NBQ * NBQ);
   ws.Yw = cv.take<double>((size_t)cap * NBQ * n);
-  ws.Y2 = cv.take<double>((size_t)cap * NBQ * n);
 }
 
 int tridiagonalise_legacy(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
@@ -893,7 +816,7 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
     GSCF_TRY(launch_gemm(true, false, gp, batch * nblocks, NBQ, NBQ, st));
   }
-  larft_kernel<<<dim3(nblocks, batch), 256, 2 * NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);
+  larft_kernel<<<dim3(nblocks, batch), 4 * NBQ, NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);
   bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 1, batch, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
@@ -944,9 +867,7 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   static bool cfg = false;
   if (!cfg) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       2 * NBQ * (NBQ + 1) * (int)sizeof(double)));
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(wy_trsm_kernel<NBQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (NBQ * (NBQ + 1) + NBQ * 128) * (int)sizeof(double)));
+                                       NBQ * (NBQ + 1) * (int)sizeof(double)));
     cfg = true;
   }
   // capacity: derive from the workspace size so that batch_map indices stay in range
