@@ -62,14 +62,14 @@ size_t syev_worksize(int n, int batch, int method) {
 int syev_batched(int method, int n, double* A, int lda, long long strideA, double* w,
                  long long stride_w, double* Z, int ldz, long long strideZ, int batch,
                  const int* batch_map, void* work, size_t work_bytes, int* info_dev,
-                 cudaStream_t st) {
+                 cudaStream_t st, int nvec) {
   const int m = resolve_eig_method(method, n);
   if (m < 0) return GSCF_B200_ERR_INVALID_ARG;
   if (m == GSCF_B200_EIG_JACOBI)
     return jacobi_syev_batched(n, A, lda, strideA, w, stride_w, Z, ldz, strideZ, batch, batch_map,
                                info_dev, st);
   return tridiag_dc_syev_batched(n, A, lda, strideA, w, stride_w, Z, ldz, strideZ, batch,
-                                 batch_map, work, work_bytes, info_dev, st);
+                                 batch_map, work, work_bytes, info_dev, st, nvec);
 }
 
 }  // namespace gscfb

@@ -20,10 +20,12 @@ struct DcPlan;
 size_t tridiag_dc_worksize(int n, int batch);
 // A (n x n, ld lda, FULL symmetric storage, destroyed) -> w ascending, Z (n x n) eigenvectors.
 // batch_map (optional): entry z works on matrix batch_map[z] of every strided array.
+// nvec: only the eigenvectors of the nvec lowest eigenvalues are back-transformed (n_eigenpairs < n, ScfBase.hh:87);
+// all n eigenvalues are always returned.
 int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double* w,
                             long long stride_w, double* Z, int ldz, long long strideZ, int batch,
                             const int* batch_map, void* work, size_t work_bytes, int* info_dev,
-                            cudaStream_t st);
+                            cudaStream_t st, int nvec = -1);
 
 // Mirror the lower triangle into the upper one (batched).
 int symmetrise_from_lower(double* A, int lda, long long strideA, int n, int batch,
@@ -35,6 +37,6 @@ size_t syev_worksize(int n, int batch, int method);
 int syev_batched(int method, int n, double* A, int lda, long long strideA, double* w,
                  long long stride_w, double* Z, int ldz, long long strideZ, int batch,
                  const int* batch_map, void* work, size_t work_bytes, int* info_dev,
-                 cudaStream_t st);
+                 cudaStream_t st, int nvec = -1);
 
 }  // namespace gscfb

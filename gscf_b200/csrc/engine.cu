@@ -187,13 +187,14 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
     h.sA = e->sx_stride ? e->pstride : 0; h.sB = e->pstride; h.sC = e->pstride; h.batch_map = e->act_p;
     GSCF_TRY(launch_gemm(false, false, h, nact, n, n, e->stream));
   }
+  const int nv = (e->neig > 0 && e->neig < n) ? e->neig : n;
   GSCF_TRY(syev_batched(e->eig_method, n, e->Aeig, ld, e->mstride, e->orben_cur(), n, e->Zeig, ld,
-                        e->mstride, nm, e->act_m, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream));
+                        e->mstride, nm, e->act_m, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream, nv));
   for (int b = 0; b < e->nblk; ++b) {
-    GemmParams g = gemm_params(n, n, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Zeig + b * e->mstride, ld,
+    GemmParams g = gemm_params(n, nv, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Zeig + b * e->mstride, ld,
                                0.0, e->Ccur() + b * e->mstride, ld);
     g.sA = e->sx_stride ? e->pstride : 0; g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, false, g, nact, n, n, e->stream));
+    GSCF_TRY(launch_gemm(false, false, g, nact, n, nv, e->stream));
   }
   e->have_coeff = true;
   return GSCF_B200_OK;
@@ -403,9 +404,16 @@ int check_ready(Engine* e, const gscf_b200_params* prm) {
   if (!e || !prm) return GSCF_B200_ERR_INVALID_ARG;
   if (!e->have_overlap) { set_last_error("overlap not set"); return GSCF_B200_ERR_INVALID_STATE; }
   if (e->cur_slot < 0) { set_last_error("problem matrix not set"); return GSCF_B200_ERR_INVALID_STATE; }
+  // n_eigenpairs (ScfBase.hh:87, :315-316): the lowest k pairs.  All n eigenvalues are still computed (dense
+  // tridiagonal D&C); what k < n saves is the back-transformation and X Z of the n - k unwanted vectors.
+  e->neig = e->n;
   if (prm->n_eigenpairs >= 0 && prm->n_eigenpairs < e->n) {
-    set_last_error("n_eigenpairs < n is not implemented (SURVEY 8f item 3)");
-    return GSCF_B200_ERR_NOT_IMPLEMENTED;
+    const int kmin = std::max(e->occ[0], e->nblk > 1 ? e->occ[1] : 0);
+    if (prm->n_eigenpairs < kmin) {
+      set_last_error("n_eigenpairs is smaller than the number of occupied orbitals");
+      return GSCF_B200_ERR_INVALID_ARG;
+    }
+    e->neig = (int)prm->n_eigenpairs;
   }
   for (int p = 0; p < e->P; ++p)
     if (e->status[p] != GSCF_B200_OK) { set_last_error("cannot solve a failed state"); return GSCF_B200_ERR_INVALID_STATE; }
@@ -1034,6 +1042,8 @@ int gscf_b200_get_energies(gscf_b200_engine* e, double* a, double* b) {
 }
 int gscf_b200_get_n_mtx_applies(gscf_b200_engine* e, long long* v) { if (!e || !v) return GSCF_B200_ERR_INVALID_ARG; std::copy(e->n_mtx_applies.begin(), e->n_mtx_applies.end(), v); return GSCF_B200_OK; }
 int gscf_b200_get_damping_coeff(gscf_b200_engine* e, double* v) { if (!e || !v) return GSCF_B200_ERR_INVALID_ARG; std::copy(e->damp.begin(), e->damp.end(), v); return GSCF_B200_OK; }
+
+int gscf_b200_get_n_eigenpairs(gscf_b200_engine* e) { return e ? ((e->neig > 0 && e->neig < e->n) ? e->neig : e->n) : -1; }
 
 int gscf_b200_get_orben(gscf_b200_engine* e, double* w) {
   if (!e || !w) return GSCF_B200_ERR_INVALID_ARG;

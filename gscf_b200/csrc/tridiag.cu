@@ -803,8 +803,9 @@ __global__ void bt_desc_kernel(TrdWs ws, int which, int batch, const int* __rest
 // Everything that does not depend on Z is done up front for all blocks at once (V, G_b, T_b, W_b = V_b T_b: four
 // launches); the sequential part is two GEMMs per block:  Y = V_b^T Z,  Z -= W_b Y.
 int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& ws, double* Z, int ldz,
-                   long long sZ, int batch, const int* map, cudaStream_t st) {
+                   long long sZ, int batch, const int* map, cudaStream_t st, int nvec) {
   if (n < 2) return GSCF_B200_OK;
+  const int nz = (nvec > 0 && nvec < n) ? nvec : n;  // columns of Z that are wanted
   const int nref = n - 1;  // reflectors 0..n-2
   const int nblocks = ws.nbq;
   extract_v_all_kernel<<<dim3(std::max(1, std::min(8, ceil_div(n, 256))), n, batch), 256, 0, st>>>(A, lda, sA, ws, map);
@@ -832,14 +833,14 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     const double* Vb = ws.Vf + (size_t)j0 * ws.ld + j0 + 1;
     const double* Wb = ws.Wf + (size_t)j0 * ws.ld + j0 + 1;
     // Y = V_b^T Z(j0+1:, :)   (pw x n, ld NBQ)
-    GemmParams y = gemm_params(pw, n, m, 1.0, Vb, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
+    GemmParams y = gemm_params(pw, nz, m, 1.0, Vb, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
     y.sA = (long long)ws.ld * n; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
     const int splits = batch >= 16 ? 1 : std::max(1, std::min(8, m / 128));  // long-k TN product: split-k
     GSCF_TRY(launch_gemm_splitk(true, false, y, batch, splits, ws.SK, st));
     // Z(j0+1:, :) -= W_b Y
-    GemmParams u = gemm_params(m, n, pw, -1.0, Wb, ws.ld, ws.Yw, NBQ, 1.0, Z + j0 + 1, ldz);
+    GemmParams u = gemm_params(m, nz, pw, -1.0, Wb, ws.ld, ws.Yw, NBQ, 1.0, Z + j0 + 1, ldz);
     u.sA = (long long)ws.ld * n; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;
-    GSCF_TRY(launch_gemm(false, false, u, batch, m, n, st));
+    GSCF_TRY(launch_gemm(false, false, u, batch, m, nz, st));
   }
   return GSCF_B200_OK;
 }
@@ -856,7 +857,7 @@ size_t tridiag_dc_worksize(int n, int batch) {
 
 int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double* w, long long stride_w,
                             double* Z, int ldz, long long strideZ, int batch, const int* batch_map, void* work,
-                            size_t work_bytes, int* info_dev, cudaStream_t st) {
+                            size_t work_bytes, int* info_dev, cudaStream_t st, int nvec) {
   if (batch <= 0 || n <= 0) return GSCF_B200_OK;
   // the workspace is indexed like the matrices (by batch_map[z] when given): capacity = what
   // the caller sized it for; we only check the lower bound for `batch` entries
@@ -886,7 +887,7 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st));
   phase_mark(PH_STEDC, false, st);
   phase_mark(PH_BACKTRANSFORM, true, st);
-  GSCF_TRY(back_transform(n, A, lda, strideA, ws, Z, ldz, strideZ, batch, batch_map, st));
+  GSCF_TRY(back_transform(n, A, lda, strideA, ws, Z, ldz, strideZ, batch, batch_map, st, nvec));
   phase_mark(PH_BACKTRANSFORM, false, st);
   return GSCF_B200_OK;
 }

@@ -104,6 +104,7 @@ SIGNATURES = {
     "gscf_b200_get_energies": (C.c_int, [_P, _D, _D]),
     "gscf_b200_get_n_mtx_applies": (C.c_int, [_P, C.POINTER(_LL)]),
     "gscf_b200_get_orben": (C.c_int, [_P, _D]),
+    "gscf_b200_get_n_eigenpairs": (C.c_int, [_P]),
     "gscf_b200_get_coeff": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_prev_coeff": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_fock": (C.c_int, [_P, _D, C.c_int]),

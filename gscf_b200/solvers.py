@@ -420,9 +420,14 @@ class Engine:
         return res
 
     # used by ScfState while hooks run
+    def n_eigenpairs(self) -> int:
+        """Eigenpairs kept by the last solve (ScfBaseKeys.n_eigenpairs, ScfBase.hh:87)."""
+        return int(L.lib.gscf_b200_get_n_eigenpairs(self.handle))
+
     def refresh_eigensolution(self, state):
-        w = self.orben()[0]
-        Cm = self.get_matrix("coeff")[0]
+        k = self.n_eigenpairs()
+        w = self.orben()[0][..., :k]
+        Cm = self.get_matrix("coeff")[0][..., :k]
         if self.nblk == 1:
             state._esol = Eigensolution(w[0], Cm[0])
         else:

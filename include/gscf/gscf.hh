@@ -329,9 +329,12 @@ struct ScfBase<State>::Driver {
   void mirror_eigensolution(const double* C, const double* w, int it) {
     if (mirrored_iter == it) return;
     typename state_type::esoln_type es;
-    es.evalues().assign(w, w + n);
-    auto mv = std::make_shared<lazyten::MultiVector<vector_type>>(n, n);
-    for (size_t j = 0; j < n; ++j)
+    // n_eigenpairs (ScfBase.hh:87): the eigensolution holds the k lowest pairs only
+    const int kq = gscf_b200_get_n_eigenpairs(eng);
+    const size_t k = (kq > 0 && (size_t)kq < n) ? (size_t)kq : n;
+    es.evalues().assign(w, w + k);
+    auto mv = std::make_shared<lazyten::MultiVector<vector_type>>(n, k);
+    for (size_t j = 0; j < k; ++j)
       for (size_t i = 0; i < n; ++i) (*mv)[j](i) = C[j * n + i];
     es.evectors_ptr = mv;
     state->push_new_eigensolution(std::move(es), {0, 0});
@@ -438,7 +441,6 @@ void ScfBase<State>::run_engine(state_type& state, Method method) const {
   const krims::Range<size_t> occ_a = pm0.indices_orbspace(OrbitalSpace::OCC_ALPHA);
   const krims::Range<size_t> occ_b = pm0.indices_orbspace(OrbitalSpace::OCC_BETA);
   assert_implemented(occ_a == occ_b);  // restricted problems through the C++ layer (see header note)
-  assert_implemented(n_eigenpairs == lazyten::Constants<size_type>::all || n_eigenpairs >= n);
 
   Driver drv{this, &state};
   drv.n = n;
@@ -475,6 +477,7 @@ void ScfBase<State>::run_engine(state_type& state, Method method) const {
   gscf_b200_default_params(&prm);
   prm.max_iter = (int)this->max_iter;
   prm.max_error_norm = max_error_norm;
+  prm.n_eigenpairs = (n_eigenpairs == lazyten::Constants<size_type>::all || n_eigenpairs >= n) ? -1 : (long long)n_eigenpairs;
   b200_fill_params(prm);
   int st = GSCF_B200_OK;
   switch (method) {

@@ -200,7 +200,7 @@ typedef struct gscf_b200_config {
  * diis_n_prev_steps, toda_n_prev_steps, toda_min_fock_prefactor). */
 typedef struct gscf_b200_params {
   int max_iter;                /* 100 */
-  long long n_eigenpairs;      /* -1 = all (only "all" is implemented) */
+  long long n_eigenpairs;      /* -1 = all; k < n: the k lowest pairs (k >= occupied orbitals) */
   double max_error_norm;       /* 5e-7 */
   int diis_n_prev_steps;       /* 4 */
   int toda_n_prev_steps;       /* 2 (must be 2, TruncatedOptDampScf.hh:243) */
@@ -248,6 +248,9 @@ int gscf_b200_get_error_norm(gscf_b200_engine* e, double* err);        /* [P] */
 int gscf_b200_get_energies(gscf_b200_engine* e, double* e1, double* e2);/* [P] each */
 int gscf_b200_get_n_mtx_applies(gscf_b200_engine* e, long long* n);    /* [P] */
 int gscf_b200_get_orben(gscf_b200_engine* e, double* orben);           /* [P][n_blocks][n] */
+/* Eigenpairs kept by the last solve (ScfBaseKeys::n_eigenpairs, ScfBase.hh:87): the first k entries of every orben
+ * row and the first k columns of every coefficient block are the eigensolution; the rest is unspecified. */
+int gscf_b200_get_n_eigenpairs(gscf_b200_engine* e);
 int gscf_b200_get_coeff(gscf_b200_engine* e, double* C, int ld);       /* [P][n_blocks] n x n */
 int gscf_b200_get_prev_coeff(gscf_b200_engine* e, double* C, int ld);
 int gscf_b200_get_fock(gscf_b200_engine* e, double* F, int ld);

@@ -146,7 +146,8 @@ def _run_synthetic(G, n, o, aux, which, seed=0, params=None, n_beta=None, eig=0)
     try:
         assert st == L.OK, L.last_error()
         out = dict(n_iter=int(eng.n_iter()[0]), e=eng.energies(), w=eng.orben()[0], D=eng.get_matrix("density")[0],
-                   err=float(eng.error_norm()[0]), trace=eng.trace(0))
+                   err=float(eng.error_norm()[0]), trace=eng.trace(0), C=eng.get_matrix("coeff")[0],
+                   n_eigenpairs=eng.n_eigenpairs())
     finally:
         eng.close()
         fock.close()
@@ -262,3 +263,21 @@ def test_synthetic_parity_large_path(G, n, o, aux, m):
     assert np.abs(got["w"][0] - ref.orben[0]).max() < TOL_EPS
     assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < TOL_D
     np.testing.assert_allclose(got["trace"][1], ref.trace_error, rtol=1e-5, atol=1e-12)
+
+
+def test_n_eigenpairs_partial(G):
+    """ScfBaseKeys.n_eigenpairs < n (ScfBase.hh:87,315-316): same iterations / energy / occupied orbitals as the full
+    solve; the eigensolution holds k pairs.  Parity unpinned (the reference has no test for it): checked against the
+    full-spectrum path and the oracle."""
+    n, o, aux, k = 160, 20, 8, 40
+    full = _run_synthetic(G, n, o, aux, "diis", params={"diis_n_prev_steps": 4})
+    part = _run_synthetic(G, n, o, aux, "diis", params={"diis_n_prev_steps": 4, "n_eigenpairs": k})
+    assert part["n_iter"] == full["n_iter"]
+    assert abs(part["e"][0][0] + part["e"][1][0] - full["e"][0][0] - full["e"][1][0]) < TOL_E
+    assert np.abs(part["w"][0, :k] - full["w"][0, :k]).max() < TOL_EPS
+    Dp = part["C"][0][:, :o] @ part["C"][0][:, :o].T
+    Df = full["C"][0][:, :o] @ full["C"][0][:, :o].T
+    assert np.linalg.norm(Dp - Df) < TOL_D
+    assert part["n_eigenpairs"] == k and full["n_eigenpairs"] == n
+    with pytest.raises(Exception):
+        _run_synthetic(G, n, o, aux, "diis", params={"n_eigenpairs": o - 1})
