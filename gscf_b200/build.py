@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgscf_b200.so")
-SOURCES = ["gemm.cu", "stream.cu", "jacobi.cu", "eig.cu", "tridiag.cu", "stedc.cu", "fock_df.cu",
+SOURCES = ["gemm.cu", "stream.cu", "jacobi.cu", "eig.cu", "tridiag.cu", "stedc.cu", "chol.cu", "fock_df.cu",
            "engine.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <limits>
 
+#include "chol.cuh"
 #include "eig.cuh"
 #include "gemm.cuh"
 #include "smallsolve.hpp"
@@ -175,18 +176,23 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
                         (long long)n * e->nblk, 1.0, n * e->nblk, 1, nact, e->act_p, e->stream));
   }
   // matrix-level strides: Fd may live in the ring (problem stride != nblk*mstride); handle per block
+  const bool tri = e->ortho == 1;  // X = L^-1 lower triangular:  A' = X Fd X^T  (else X symmetric: A' = X Fd X)
   for (int b = 0; b < e->nblk; ++b) {
-    // T = Fd * X
+    // T = Fd * X^T
     GemmParams g = gemm_params(n, n, n, 1.0, Fd + b * e->mstride, ld, e->X + (e->sx_stride ? b * e->mstride : 0), ld,
                                0.0, e->Tmp + b * e->mstride, ld);
     g.sA = fd_pstride; g.sB = e->sx_stride ? e->pstride : 0; g.sC = e->pstride; g.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, false, g, nact, n, n, e->stream));
+    g.ktri = tri ? 1 : 0;  // X^T(k, j) = X(j, k) = 0 for k > j
+    GSCF_TRY(launch_gemm(false, tri, g, nact, n, n, e->stream));
     // A' = X * T
     GemmParams h = gemm_params(n, n, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Tmp + b * e->mstride, ld,
                                0.0, e->Aeig + b * e->mstride, ld);
     h.sA = e->sx_stride ? e->pstride : 0; h.sB = e->pstride; h.sC = e->pstride; h.batch_map = e->act_p;
+    h.ktri = tri ? 2 : 0;  // X(i, k) = 0 for k > i
+    h.lower_only = tri ? 1 : 0;  // the eigensolver symmetrises from the lower triangle
     GSCF_TRY(launch_gemm(false, false, h, nact, n, n, e->stream));
   }
+  if (tri) GSCF_TRY(symmetrise_from_lower(e->Aeig, ld, e->mstride, n, nm, e->act_m, e->stream));
   const int nv = (e->neig > 0 && e->neig < n) ? e->neig : n;
   GSCF_TRY(syev_batched(e->eig_method, n, e->Aeig, ld, e->mstride, e->orben_cur(), n, e->Zeig, ld,
                         e->mstride, nm, e->act_m, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream, nv));
@@ -194,7 +200,8 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
     GemmParams g = gemm_params(n, nv, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Zeig + b * e->mstride, ld,
                                0.0, e->Ccur() + b * e->mstride, ld);
     g.sA = e->sx_stride ? e->pstride : 0; g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, false, g, nact, n, nv, e->stream));
+    g.ktri = tri ? 3 : 0;  // C = X^T Z:  X^T(i, k) = X(k, i) = 0 for k < i
+    GSCF_TRY(launch_gemm(tri, false, g, nact, n, nv, e->stream));
   }
   e->have_coeff = true;
   return GSCF_B200_OK;
@@ -532,6 +539,14 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
   auto A = [&](auto** ptr, size_t cnt) { if (st == GSCF_B200_OK) st = dev_alloc(ptr, cnt); };
   A(&e->S, nS * e->mstride);
   A(&e->X, nS * e->mstride);
+  {
+    const char* oe = getenv("GSCF_B200_ORTHO");
+    e->ortho = (oe && (oe[0] == 'l' || oe[0] == 'L' || oe[0] == '0')) ? 0 : 1;
+    void* cw = nullptr;
+    if (cudaMalloc(&cw, cholesky_inverse_worksize(e->n, (int)nS)) != cudaSuccess) cw = nullptr;
+    e->cholwork = static_cast<double*>(cw);
+    if (!cw) e->ortho = 0;
+  }
   A(&e->Fring, P * (e->M + 1) * e->pstride);
   A(&e->Ering, P * e->M * e->pstride);
   A(&e->Fdiag, P * e->pstride);
@@ -588,6 +603,7 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
 void gscf_b200_engine_destroy(gscf_b200_engine* e) {
   if (!e) return;
   if (e->stream) cudaStreamSynchronize(e->stream);
+  cudaFree(e->cholwork);
   cudaFree(e->S); cudaFree(e->X); cudaFree(e->Fring); cudaFree(e->Ering); cudaFree(e->Fdiag);
   cudaFree(e->Cbuf); cudaFree(e->orben); cudaFree(e->D); cudaFree(e->Aeig); cudaFree(e->Zeig);
   cudaFree(e->Tmp); cudaFree(e->errwork); cudaFree(e->gram); cudaFree(e->coeff); cudaFree(e->dots);
@@ -617,33 +633,44 @@ int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int meml
       for (int b = 0; b < e->nblk; ++b)
         GSCF_TRY(copy_in(e, e->S + p * e->pstride + b * e->mstride, e->mstride, S + (size_t)p * ld * n, ld, memloc, 1));
   }
-  // X = S^-1/2 = U diag(w^-1/2) U^T, through our own eigensolver (Loewdin orthogonalisation).
   const int nm = e->cfg.shared_overlap ? 1 : e->P * e->nblk;
-  // Aeig <- S (the eigensolver destroys its input)
+  // Aeig <- S (both set-ups destroy their input)
   GSCF_CUDA_TRY(cudaMemcpyAsync(e->Aeig, e->S, (size_t)nm * e->mstride * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
-  double* wtmp = e->orben;  // scratch: overwritten by the first eigensolve anyway
-  GSCF_TRY(syev_batched(e->eig_method, n, e->Aeig, e->ld, e->mstride, wtmp, n, e->Zeig, e->ld, e->mstride,
-                        nm, nullptr, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream));
-  // U~ = U diag(w^-1/4);  X = U~ U~^T
-  GSCF_TRY(scale_columns_pow(e->Tmp, e->ld, e->mstride, e->Zeig, e->ld, e->mstride, wtmp, n, 1, n, n, nm, e->stream));
-  GSCF_TRY(gemm_batched(false, true, n, n, n, 1.0, e->Tmp, e->ld, e->mstride, e->Tmp, e->ld, e->mstride,
-                        0.0, e->X, e->ld, e->mstride, nm, nullptr, e->stream));
   std::vector<int> info(nm);
-  std::vector<double> wh((size_t)nm * n);
+  std::vector<double> wh;
+  if (e->ortho == 1) {
+    // Cholesky: S = L L^T, X = L^-1 (chol.cu); every later product with X is triangular
+    GSCF_TRY(cholesky_inverse_batched(n, e->Aeig, e->ld, e->mstride, e->Tmp, e->ld, e->mstride, e->X, e->ld, e->mstride,
+                                      e->cholwork, nm, e->eiginfo, e->stream));
+  } else {
+    // Loewdin: X = S^-1/2 = U diag(w^-1/2) U^T, through our own eigensolver
+    double* wtmp = e->orben;  // scratch: overwritten by the first eigensolve anyway
+    GSCF_TRY(syev_batched(e->eig_method, n, e->Aeig, e->ld, e->mstride, wtmp, n, e->Zeig, e->ld, e->mstride,
+                          nm, nullptr, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream));
+    // U~ = U diag(w^-1/4);  X = U~ U~^T
+    GSCF_TRY(scale_columns_pow(e->Tmp, e->ld, e->mstride, e->Zeig, e->ld, e->mstride, wtmp, n, 1, n, n, nm, e->stream));
+    GSCF_TRY(gemm_batched(false, true, n, n, n, 1.0, e->Tmp, e->ld, e->mstride, e->Tmp, e->ld, e->mstride,
+                          0.0, e->X, e->ld, e->mstride, nm, nullptr, e->stream));
+    wh.resize((size_t)nm * n);
+    GSCF_CUDA_TRY(cudaMemcpyAsync(wh.data(), wtmp, wh.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  }
   GSCF_CUDA_TRY(cudaMemcpyAsync(info.data(), e->eiginfo, nm * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  GSCF_CUDA_TRY(cudaMemcpyAsync(wh.data(), wtmp, wh.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   cudaEventRecord(ov_b, e->stream);
   GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
   {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ov_a, ov_b);
-    e->overlap_ms = ms;  // orthogonaliser set-up (H2D of S + S^-1/2), reported as phase 7
+    e->overlap_ms = ms;  // orthogonaliser set-up (H2D of S + X), reported as phase 7
     cudaEventDestroy(ov_a);
     cudaEventDestroy(ov_b);
   }
   for (int i = 0; i < nm; ++i) {
-    if (info[i] != 0) { set_last_error("eigensolver failed on the overlap matrix"); return GSCF_B200_ERR_EIGENSOLVER; }
-    if (!(wh[(size_t)i * n] > 0.0)) { set_last_error("overlap matrix is not positive definite"); return GSCF_B200_ERR_INVALID_ARG; }
+    if (e->ortho == 1) {
+      if (info[i] != 0) { set_last_error("overlap matrix is not positive definite"); return GSCF_B200_ERR_INVALID_ARG; }
+    } else {
+      if (info[i] != 0) { set_last_error("eigensolver failed on the overlap matrix"); return GSCF_B200_ERR_EIGENSOLVER; }
+      if (!(wh[(size_t)i * n] > 0.0)) { set_last_error("overlap matrix is not positive definite"); return GSCF_B200_ERR_INVALID_ARG; }
+    }
   }
   e->have_overlap = true;
   return GSCF_B200_OK;

@@ -15,6 +15,8 @@ struct gscf_b200_engine {
   int omax = 0;
   long long mstride = 0, pstride = 0;  // elements per matrix / per problem
   int eig_method = 0;
+  int ortho = 1;             // orthogonaliser: 0 Loewdin X = S^-1/2 (symmetric), 1 Cholesky X = L^-1 (lower triangular)
+  double* cholwork = nullptr;
   int neig = 0;  // eigenpairs kept per block (n_eigenpairs, ScfBase.hh:87); 0 = not yet set = all
   cudaStream_t stream = nullptr;
   bool owns_stream = false;

@@ -81,6 +81,7 @@ dgemm_dmma_kernel(const GemmParams p) {
   }
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (m0 >= m || n0 >= n) return;
+  if (p.lower_only && n0 >= m0 + BM) return;  // tile strictly above the diagonal
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp % (BM / WM)) * WM, wn = (warp / (BM / WM)) * WN;
@@ -100,6 +101,10 @@ dgemm_dmma_kernel(const GemmParams p) {
     const int per = (KT + p.ksplit - 1) / p.ksplit;
     T0 = split * per;
     KT = min(KT, T0 + per);
+  } else if (p.ktri != 0 && p.descs == nullptr) {
+    if (p.ktri == 1) KT = min(KT, (min(k, n0 + BN) + BK - 1) / BK);
+    else if (p.ktri == 2) KT = min(KT, (min(k, m0 + BM) + BK - 1) / BK);
+    else if (p.ktri == 3) T0 = min(KT, m0 / BK);
   }
 
   auto load_tile = [&](int stage, int t) {

@@ -32,6 +32,10 @@ struct GemmParams {
   double alpha, beta;
   const int* batch_map;   // optional: batch entry z works on problem batch_map[z]
   const GemmDesc* descs;  // optional: grouped mode, one descriptor per blockIdx.z
+  int ktri;               // triangular operand: restrict the k range of every tile (kbatch == 1, no split-k)
+                          //   1: k < n0 + BN   (op(B)(k, j) = 0 for k > j)      2: k < m0 + BM   (op(A)(i, k) = 0 for k > i)
+                          //   3: k >= m0       (op(A)(i, k) = 0 for k < i)
+  int lower_only;         // 1: skip tiles strictly above the diagonal (symmetric result, mirrored by the caller)
   int ksplit;             // > 1: split-k, blockIdx.z = entry * ksplit + split, partial tiles go to Cpart
   double* Cpart;          // [batch * ksplit][m * n] partial products (compact, ld = m)
 };
@@ -43,7 +47,7 @@ inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A
   p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
   p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
-  p.ksplit = 1; p.Cpart = nullptr;
+  p.ksplit = 1; p.Cpart = nullptr; p.ktri = 0; p.lower_only = 0;
   return p;
 }
 
