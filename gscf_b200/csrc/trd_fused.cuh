@@ -42,6 +42,9 @@ struct TfArgs {
   double *d, *e, *tau;   // [cap][n]
   unsigned* abort_flag;  // one word, zero on entry
   const int* map; int mat0; int n;
+  int dstride;           // elements between the d / e / tau arrays of consecutive matrices
+  int jstop;             // 0: reduce everything.  > 0 (even): stop after reflector jstop-1, apply it, write the trailing
+                         // matrix A(jstop:, jstop:) back - the caller continues on it with a cheaper configuration
   int cluster;           // launched as one thread-block cluster per matrix: the exchange uses the hardware cluster barrier
   int smax;              // stride of the per-warp partial sums: >= owned columns per CTA, multiple of 8
 };
@@ -136,7 +139,8 @@ trd_fused_kernel(const TfArgs a) {
 #else
 #define TF_TICK(k) do { } while (0)
 #endif
-  for (int j = -1; j <= n - 2; ++j) {
+  const int jlast = (a.jstop > 0 && a.jstop <= n - 2) ? a.jstop - 1 : n - 2;
+  for (int j = -1; j <= jlast; ++j) {
     const int first = j + 1;
     double yv[KMAX], rv[KMAX];
     TF_TICK(7);
@@ -369,7 +373,7 @@ trd_fused_kernel(const TfArgs a) {
         wv[k] = tau_j * (yv[k] - alpha_w * vr);
         av2[k] = rv[k] - vr * w_first - wv[k];
         if (r == first) {
-          if (g == 0) (a.d + q * n)[first] = av2[k];
+          if (g == 0) (a.d + q * a.dstride)[first] = av2[k];
         } else if (r == nf) {
           sbc[1] = av2[k];
         } else {
@@ -382,7 +386,7 @@ trd_fused_kernel(const TfArgs a) {
     double beta = 0.0, tau_n = 0.0, scale = 0.0;
     if (nf < n) {
       householder_scalars(sbc[1], xn2, beta, tau_n, scale);
-      if (g == 0 && tid == 0) { (a.e + q * n)[first] = beta; (a.tau + q * n)[first] = tau_n; }
+      if (g == 0 && tid == 0) { (a.e + q * a.dstride)[first] = beta; (a.tau + q * a.dstride)[first] = tau_n; }
     }
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
@@ -401,6 +405,19 @@ trd_fused_kernel(const TfArgs a) {
     double* t = svc; svc = svn; svn = t;
     tau_j = tau_n;
   }
+  if (jlast < n - 2) {
+    // hand-over: apply the pending reflector jstop-1 (svn = v, sw = w after the last swap) to my columns >= jstop and
+    // write them to global memory; A(jstop:, jstop:) is then the complete matrix of the remaining reduction
+    const int js = a.jstop;
+    const int s0 = js > g ? (js - g + G - 1) / G : 0;
+    for (int slot = s0; slot < S; ++slot) {
+      const int c = g + slot * G;
+      const double wc = sw[c], vc = svn[c];
+      const double* src = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)c * lda;
+      double* dst = A + (size_t)c * lda;
+      for (int r = js + tid; r < n; r += T) dst[r] = fma(-svn[r], wc, fma(-sw[r], vc, src[r]));
+    }
+  }
 #ifdef GSCF_TF_DEBUG_TIMING
   if ((tid == 0 || tid == T - 1) && (g == 0 || g == G - 1) && blockIdx.y == 0)
     printf("cta %d tid %d cycles/col: sweep %lld sync %lld publish %lld poll %lld dot %lld norm %lld vec %lld loop %lld\n", g, tid,
@@ -412,7 +429,7 @@ trd_fused_kernel(const TfArgs a) {
   }
 #endif
   if (!SOLO && g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
-    (a.d + q * n)[0] = __longlong_as_double(0x7ff8000000000000LL);
+    (a.d + q * a.dstride)[0] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 }  // namespace

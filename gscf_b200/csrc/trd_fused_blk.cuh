@@ -370,7 +370,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
         wv[k] = tau_j * (yv[k] - alpha_w * vr);
         av2[k] = rv[k] - vr * w_first - wv[k];
         if (r == first) {
-          if (g == 0) (a.d + q * n)[first] = av2[k];
+          if (g == 0) (a.d + q * a.dstride)[first] = av2[k];
         } else if (r == nf) {
           sbc[1] = av2[k];
         } else {
@@ -382,7 +382,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
     double beta = 0.0, tau_n = 0.0, scale = 0.0;
     if (nf < n) {
       householder_scalars(sbc[1], xn2, beta, tau_n, scale);
-      if (g == 0 && tid == 0) { (a.e + q * n)[first] = beta; (a.tau + q * n)[first] = tau_n; }
+      if (g == 0 && tid == 0) { (a.e + q * a.dstride)[first] = beta; (a.tau + q * a.dstride)[first] = tau_n; }
     }
     const int ip = j - j0;  // pending index of reflector j (>= 0 for j >= 0)
 #pragma unroll
@@ -417,7 +417,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
            tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
 #endif
   if (g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
-    (a.d + q * n)[0] = __longlong_as_double(0x7ff8000000000000LL);
+    (a.d + q * a.dstride)[0] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
 }  // namespace

@@ -350,7 +350,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.ypart = cv.take<double>((size_t)cap * ws.ncb * n);
   ws.pnorm = cv.take<double>((size_t)cap * ws.npart);
   ws.pdot = cv.take<double>((size_t)cap * ws.npart);
-  ws.bar = cv.take<unsigned>((size_t)2 * cap + 1);  // [0,cap) y counters, [cap,2cap) partial-dot counters, [2cap] abort flag
+  ws.bar = cv.take<unsigned>((size_t)4 * cap + 1);  // counters of up to three phases (trd_fused), [4cap] abort flag
   ws.VPW = cv.take<double>((size_t)cap * 2 * 32 * round_up(n, 2));
   ws.PQ = cv.take<double>((size_t)cap * 2 * 256 * 64);
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
@@ -547,47 +547,50 @@ int tf_unblocked_below() {
   return ub;
 }
 
-// returns -1 when the fused kernel does not cover the case (caller falls back to the panel kernels)
-int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
-                         cudaStream_t st) {
-  static int enabled = -1, sms = 0, g_single = 0, force_global = 0;
-  if (enabled < 0) {
-    const char* env = getenv("GSCF_B200_TRD_FUSED");
-    enabled = (env && env[0] == '0') ? 0 : 1;
-    int dev = 0, coop = 0;
+// One phase: the first `jstop` reflectors (0 = all) of the n x n matrices at A (already offset to the trailing block of an
+// earlier phase), d / e / tau offset alike.  prefer_cluster: one 16-CTA cluster per matrix even for a single matrix.
+int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& ws, double* d, double* e, double* tau,
+             unsigned* counters, int batch, const int* map, int jstop, bool prefer_cluster, cudaStream_t st) {
+  static int sms = 0, g_single = 0, force_global = 0, solo_ok = 1, t_small = 256, blocked = 1, cb = 1;
+  static bool init = false;
+  if (!init) {
+    int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop || sms < 1) enabled = 0;
     const char* ge = getenv("GSCF_B200_TF_G");
     g_single = ge ? atoi(ge) : 0;
     const char* fg = getenv("GSCF_B200_TF_GLOBAL");
     force_global = (fg && fg[0] == '1') ? 1 : 0;
+    const char* se = getenv("GSCF_B200_TF_SOLO");
+    solo_ok = (se && se[0] == '0') ? 0 : 1;
+    const char* te = getenv("GSCF_B200_TF_T");
+    t_small = te ? atoi(te) : 256;
+    const char* be = getenv("GSCF_B200_TF_BLOCKED");
+    blocked = (be && be[0] == '0') ? 0 : 1;
+    const char* ce = getenv("GSCF_B200_TF_CLUSTER_BARRIER");
+    cb = (ce && ce[0] == '0') ? 0 : 1;
+    init = true;
   }
-  if (!enabled || n < 3 || (lda & 1) || n > 8192) return -1;
-  const int np = round_up(n, 2);
   constexpr size_t kSmemMax = 220 * 1024;
-  const int g_slots = 1;
-  int g_smem = 0;                                                 // fewest CTAs with the columns in shared memory
+  int g_smem = 0;  // fewest CTAs with the columns in shared memory
   if (!force_global && n <= 2048) {
-    for (int G = g_slots; G <= sms; ++G)
+    for (int G = 1; G <= sms; ++G)
       if (tf_smem_bytes(n, G, true) <= kSmemMax) { g_smem = G; break; }
   }
   // group size and launch mode
   int G = 0;
   bool cluster = false, smem_a = false;
-  static int solo_ok = -1;
-  if (solo_ok < 0) { const char* se = getenv("GSCF_B200_TF_SOLO"); solo_ok = (se && se[0] == '0') ? 0 : 1; }
   const bool solo = solo_ok && !force_global && tf_smem_bytes(n, 1, true) <= kSmemMax;
   if (solo) {
     G = 1; smem_a = true;
-  } else if (g_smem > 0 && batch * g_smem > sms && g_smem <= 16) {
-    // more matrices than fit side by side: one thread-block cluster per matrix, scheduled by the hardware
+  } else if (g_smem > 0 && g_smem <= 16 && (prefer_cluster || batch * g_smem > sms)) {
+    // one thread-block cluster per matrix, scheduled by the hardware: batches that do not fit side by side, and the
+    // middle phase of a single reduction (the cluster barrier is cheaper than the L2 counter exchange)
     G = g_smem <= 8 ? 8 : 16;
     cluster = true; smem_a = true;
   } else {
     const int per = std::max(1, sms / std::max(1, std::min(batch, sms)));  // CTAs available per matrix
-    const int gmin = g_smem > 0 && g_smem <= per ? g_smem : g_slots;
+    const int gmin = g_smem > 0 && g_smem <= per ? g_smem : 1;
     if (gmin > sms) return -1;
     G = std::max(gmin, std::min(per, ceil_div(n, 6)));
     if (g_single > 0 && batch == 1) G = std::max(gmin, std::min(sms, g_single));
@@ -595,8 +598,6 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     smem_a = g_smem > 0 && G >= g_smem;
   }
   const size_t smem = tf_smem_bytes(n, G, smem_a);
-  static int t_small = -1;
-  if (t_small < 0) { const char* te = getenv("GSCF_B200_TF_T"); t_small = te ? atoi(te) : 256; }
   const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : (n <= 4096 ? 512 : 1024);
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
@@ -612,39 +613,87 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     if (T == 512) return tf_launch<8, false, 512>(a, G, cnt, cluster, smem, st);
     return tf_launch<8, false, 1024>(a, G, cnt, cluster, smem, st);
   };
-  static int blocked = -1;
-  if (blocked < 0) { const char* be = getenv("GSCF_B200_TF_BLOCKED"); blocked = (be && be[0] == '0') ? 0 : 1; }
-  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below() &&
-                           ceil_div(n, G) <= TF_MAXS;
+  const bool use_blocked = blocked && jstop == 0 && !smem_a && !cluster && G <= 256 && TFB_PW == 32 &&
+                           n > tf_unblocked_below() && ceil_div(n, G) <= TF_MAXS;
   if (cluster) {
     int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
                     : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
     if (mc < 1) return -1;
   }
   TfArgs a;
-  a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = ws.d; a.e = ws.e; a.tau = ws.tau;
-  a.abort_flag = ws.bar + 2 * ws.cap; a.ctr = ws.bar; a.map = map; a.mat0 = 0; a.n = n; a.smax = tf_smax(n, G);
-  {
-    static int cb = -1;
-    if (cb < 0) { const char* ce = getenv("GSCF_B200_TF_CLUSTER_BARRIER"); cb = (ce && ce[0] == '0') ? 0 : 1; }
-    a.cluster = (cluster && cb) ? 1 : 0;
-  }
-  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)2 * ws.cap + 1) * sizeof(unsigned), st));
-  phase_mark(PH_SYMV_SAMPLE, true, st);
+  a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = d; a.e = e; a.tau = tau; a.dstride = n_full;
+  a.abort_flag = ws.bar + 4 * ws.cap; a.ctr = counters; a.map = map; a.mat0 = 0; a.n = n; a.smax = tf_smax(n, G);
+  a.jstop = jstop;
+  a.cluster = (cluster && cb) ? 1 : 0;
   const int per_launch = (cluster || solo) ? 32768 : std::max(1, sms / G);
   for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
     a.mat0 = mat0;
     const int cnt = std::min(per_launch, batch - mat0);
     if (use_blocked) {
       TfbArgs ab;
-      ab.b = a; ab.VP = ws.VPW; ab.WP = ws.VPW + (size_t)ws.cap * 32 * np; ab.PQ = ws.PQ; ab.ctr2 = ws.bar + ws.cap;
-      {
-        ab.unblocked_below = tf_unblocked_below();
-      }
+      ab.b = a; ab.VP = ws.VPW; ab.WP = ws.VPW + (size_t)ws.cap * 32 * round_up(n_full, 2); ab.PQ = ws.PQ;
+      ab.ctr2 = counters + ws.cap;
+      ab.unblocked_below = tf_unblocked_below();
       GSCF_TRY(tfb_launch(ab, G, cnt, T, K, tfb_smem_bytes(n), st));
     } else {
       GSCF_TRY(launch(a, cnt));
     }
+  }
+  return GSCF_B200_OK;
+}
+
+// The reduction is recursive: once reflectors 0 .. j-1 are applied, what remains is the tridiagonalisation of the
+// trailing block A(j:, j:).  The per-column cost is the exchange between the CTAs of a group (~3 600 cycles through L2
+// for any group size, less inside a cluster, nothing for a single CTA), so the group shrinks with the matrix:
+//   all SMs (matrix in shared memory or L2)  ->  one 16-CTA cluster (order <= ~590)  ->  one CTA (order <= ~144).
+// Returns -1 when the fused kernels do not cover the case (caller falls back to the panel kernels).
+int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
+                         cudaStream_t st) {
+  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144;
+  if (enabled < 0) {
+    const char* env = getenv("GSCF_B200_TRD_FUSED");
+    enabled = (env && env[0] == '0') ? 0 : 1;
+    int dev = 0, coop = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop || sms < 1) enabled = 0;
+    // measured at n = 1024 (B200): single phase 5.39 ms per eigensolve, SOLO tail only 5.38 ms, cluster + SOLO 5.93 ms -
+    // the 16-CTA cluster's longer sweep (37 columns per CTA) costs more than its cheaper barrier saves, and one CTA
+    // still spends ~6 000 cycles per column.  Off by default; GSCF_B200_TF_PHASES=1 enables the hand-over.
+    const char* pe = getenv("GSCF_B200_TF_PHASES");
+    phases_on = (pe && pe[0] == '1') ? 1 : 0;
+    const char* tc = getenv("GSCF_B200_TF_PHASE_CLUSTER");
+    if (tc) t_cluster = atoi(tc) & ~1;
+    const char* ts = getenv("GSCF_B200_TF_PHASE_SOLO");
+    if (ts) t_solo = atoi(ts) & ~1;
+  }
+  if (!enabled || n < 3 || (lda & 1) || n > 8192) return -1;
+  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)4 * ws.cap + 1) * sizeof(unsigned), st));
+  phase_mark(PH_SYMV_SAMPLE, true, st);
+  int off = 0, phase = 0;
+  while (true) {
+    const int ns = n - off;
+    int jstop = 0;
+    // the blocked kernel (orders above tf_unblocked_below()) runs to the end: its pending panel cannot be handed over
+    if (phases_on && ns <= tf_unblocked_below() && ns <= 2048 && phase < 2) {
+      if (t_cluster > t_solo && ns > t_cluster + 64 && batch <= 8) jstop = ns - t_cluster;
+      else if (t_solo > 0 && ns > t_solo + 32) jstop = ns - t_solo;
+      jstop &= ~1;
+    }
+    const bool prefer_cluster = phases_on && phase > 0 && batch <= 8;
+    // counters: phase 0 uses [0, 2 cap) (y exchange + the blocked kernel's partial dots), phases 1, 2 one array each
+    unsigned* counters = phase == 0 ? ws.bar : ws.bar + (size_t)(phase + 1) * ws.cap;
+    const int rc = tf_phase(ns, n, A + (size_t)off * lda + off, lda, sA, ws, ws.d + off, ws.e + off, ws.tau + off, counters,
+                            batch, map, jstop, prefer_cluster, st);
+    if (rc != GSCF_B200_OK) {
+      if (rc < 0 && phase == 0) return -1;
+      if (rc < 0) { set_last_error("fused tridiagonalisation: no configuration for a trailing phase"); return GSCF_B200_ERR_CUDA; }
+      return rc;
+    }
+    if (jstop == 0) break;
+    off += jstop;
+    ++phase;
   }
   phase_mark(PH_SYMV_SAMPLE, false, st);
   return GSCF_B200_OK;

@@ -283,6 +283,8 @@ def test_syev_tridiag_dc_fock_like(env):
     (512, 12, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # clusters with the L2 counter exchange
     (130, 5, {}),                                                                   # one CTA per matrix (SOLO)
     (1024, 2, {"GSCF_B200_TF_FUSED": "0"}),                                         # previous panel kernels still work
+    (1024, 1, {"GSCF_B200_TF_PHASES": "1"}),                                        # all SMs -> 16-CTA cluster -> one CTA
+    (700, 2, {"GSCF_B200_TF_PHASES": "1", "GSCF_B200_TF_PHASE_CLUSTER": "0"}),      # hand-over to the single-CTA tail
 ])
 def test_syev_fused_variants(env, n, batch, envs):
     """Every storage / exchange variant of the fused tridiagonalisation (trd_fused.cuh, trd_fused_blk.cuh)."""
