@@ -22,6 +22,7 @@ metric  scf_iterations_per_s = SCF iterations / time in the SCF path, Fock build
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -233,25 +234,35 @@ def run_ours(args, w):
     eng.set_fock_device(fn_ptr, ctx)
     eng.set_phase_timing(True)
 
+    # pinned HOST result buffers: the C ABI getters copy straight into them (what a C++ host would do)
+    C_host = torch.empty((P_local * nblk, n, n), dtype=torch.float64).pin_memory()
+    w_host = torch.empty((P_local * nblk, n), dtype=torch.float64).pin_memory()
+    e_host = torch.empty((2, P_local), dtype=torch.float64).pin_memory()
+    _D = ctypes.POINTER(ctypes.c_double)
+
+    def _p(t):
+        return ctypes.cast(t.data_ptr(), _D)
+
     def one_step():
-        """One solve through the public API with HOST inputs; returns per-step measurements."""
+        """One solve through the public C ABI with HOST inputs and HOST outputs; returns per-step measurements."""
         flush.zero_()  # L2 flush between timed iterations
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         L.check(L.lib.gscf_b200_set_overlap(eng.handle, S_host.data_ptr(), n, L.HOST))
         L.check(L.lib.gscf_b200_set_guess_from_matrix(eng.handle, H_host.data_ptr(), n, L.HOST))
         st = eng.solve("diis", params)
-        its = eng.n_iter()
-        e1, e2 = eng.energies()
-        w_ = eng.orben()
-        Cm = eng.get_matrix("coeff")
+        L.check(L.lib.gscf_b200_get_energies(eng.handle, _p(e_host[0]), _p(e_host[1])))
+        L.check(L.lib.gscf_b200_get_orben(eng.handle, _p(w_host)))
+        L.check(L.lib.gscf_b200_get_coeff(eng.handle, _p(C_host), n))
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        its = eng.n_iter()
+        e1, e2 = e_host[0].numpy().copy(), e_host[1].numpy().copy()
         scf_ms, fock_ms = eng.timings()
         ph = eng.phase_timings()
         return dict(status=st, iters=its.copy(), e=(e1 + e2).copy(), conv=eng.converged().copy(), wall=wall,
                     scf_ms=scf_ms, fock_ms=fock_ms, overlap_ms=ph["overlap"], ph=ph,
-                    d2h=w_.nbytes + Cm.nbytes + e1.nbytes + e2.nbytes)
+                    d2h=C_host.numel() * 8 + w_host.numel() * 8 + e_host.numel() * 8)
 
     for _ in range(args.warmup):
         one_step()
