@@ -91,7 +91,12 @@ inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
 
 // SOLO: one CTA owns the whole matrix (n <= ~150, batches of small problems): the exchange is two shared-memory
 // vectors, no counter, no global round trip.
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false>
+// REGA: the CTA's columns live in REGISTERS (n <= 1024 on >= n/8 CTAs: 8 columns x 4 rows per thread): the sweep was
+// bound by shared-memory bandwidth (17 LDS/STS.128 per row pair), with the matrix in registers it only reads the
+// three vectors.  Thread t owns rows 2 (t + T p), 2 (t + T p) + 1, p < TF_RP, of every owned column.
+constexpr int TF_RS = 8;  // owned columns per CTA in registers
+constexpr int TF_RP = 2;  // row pairs per thread
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
 __global__ void __launch_bounds__(T, 1)
 trd_fused_kernel(const TfArgs a) {
   const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -124,6 +129,21 @@ trd_fused_kernel(const TfArgs a) {
       const double* src = A + (size_t)(g + s * G) * lda;
       for (int r = tid; r < np; r += T) sAc[(size_t)s * np + r] = r < n ? src[r] : 0.0;
     }
+  }
+  double2 ra[REGA ? TF_RS : 1][REGA ? TF_RP : 1];
+  if (REGA) {
+#pragma unroll
+    for (int s = 0; s < TF_RS; ++s)
+#pragma unroll
+      for (int p = 0; p < TF_RP; ++p) {
+        const int c = g + s * G, r = 2 * (tid + T * p);
+        double2 v = make_double2(0.0, 0.0);
+        if (s < S && r < n) {
+          v.x = A[(size_t)c * lda + r];
+          if (r + 1 < n) v.y = A[(size_t)c * lda + r + 1];
+        }
+        ra[REGA ? s : 0][REGA ? p : 0] = v;
+      }
   }
   __syncthreads();
 
@@ -159,7 +179,56 @@ trd_fused_kernel(const TfArgs a) {
       double* Xy = X + (size_t)(j & 1) * 2 * np;
       double* Xr = Xy + np;
       const bool pub_raw = (g + s0 * G == first);  // I own column j+1: its updated values are the raw column
-      if (SOLO) {
+      if (REGA) {
+        static_assert(!REGA || TF_RS == TF_CG, "one register group");
+        double acc[TF_CG], wc[TF_CG], vc[TF_CG];
+#pragma unroll
+        for (int u = 0; u < TF_CG; ++u) {
+          const int c = g + u * G;
+          acc[u] = 0.0;
+          wc[u] = u < S ? sw[c] : 0.0;
+          vc[u] = u < S ? svn[c] : 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < TF_RP; ++p) {
+          const int r = 2 * (tid + T * p);
+          if (r + 1 >= first && r < np) {
+            const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
+            const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
+            const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
+#pragma unroll
+            for (int u = 0; u < TF_CG; ++u) {
+              if (u >= s0 && u < S) {
+                double2 x = ra[REGA ? u : 0][REGA ? p : 0];
+                x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+                x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+                ra[REGA ? u : 0][REGA ? p : 0] = x;
+                if (pub_raw && u == s0) *reinterpret_cast<double2*>(Xr + r) = x;
+                acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
+              }
+            }
+          }
+        }
+        {
+          const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+          double a4[4], a2[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+          const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+          if ((lane & 3) == 0 && u >= s0 && u < S) spart[warp * smax + u] = a1;
+        }
+      } else if (SOLO) {
         // few rows (n <= ~150): one WARP per group of 8 columns, lanes over the row pairs - the block-wide mapping
         // below would leave three quarters of the threads without a row
         for (int sg = s0 + warp * TF_CG; sg < S; sg += NW * TF_CG) {
@@ -415,7 +484,22 @@ trd_fused_kernel(const TfArgs a) {
       const double wc = sw[c], vc = svn[c];
       const double* src = SMEM_A ? sAc + (size_t)slot * np : A + (size_t)c * lda;
       double* dst = A + (size_t)c * lda;
-      for (int r = js + tid; r < n; r += T) dst[r] = fma(-svn[r], wc, fma(-sw[r], vc, src[r]));
+      if (!REGA)
+        for (int r = js + tid; r < n; r += T) dst[r] = fma(-svn[r], wc, fma(-sw[r], vc, src[r]));
+    }
+    if (REGA) {
+#pragma unroll
+      for (int u = 0; u < TF_RS; ++u)
+#pragma unroll
+        for (int p = 0; p < TF_RP; ++p) {
+          const int c = g + u * G, r = 2 * (tid + T * p);
+          if (u >= s0 && u < S) {
+            const double2 x = ra[REGA ? u : 0][REGA ? p : 0];
+            const double wc = sw[c], vc = svn[c];
+            if (r >= js && r < n) A[(size_t)c * lda + r] = fma(-svn[r], wc, fma(-sw[r], vc, x.x));
+            if (r + 1 >= js && r + 1 < n) A[(size_t)c * lda + r + 1] = fma(-svn[r + 1], wc, fma(-sw[r + 1], vc, x.y));
+          }
+        }
     }
   }
 #ifdef GSCF_TF_DEBUG_TIMING

@@ -460,10 +460,10 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 }
 
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
   static bool configured = false;
-  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO>;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA>;
   if (!configured) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -581,8 +581,16 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   int G = 0;
   bool cluster = false, smem_a = false;
   const bool solo = solo_ok && !force_global && tf_smem_bytes(n, 1, true) <= kSmemMax;
+  static int batch_global = -1;
+  // measured (128 matrices of order 512, whole eigensolve): 16-CTA clusters in shared memory 43.6 ms, clusters of 4
+  // working in L2 39.5 ms (37 matrices in flight instead of 8)
+  if (batch_global < 0) { const char* bg = getenv("GSCF_B200_TF_BATCH_GLOBAL"); batch_global = bg ? atoi(bg) : 4; }
   if (solo) {
     G = 1; smem_a = true;
+  } else if (batch_global > 0 && batch * g_smem > sms && g_smem > batch_global && n <= 2048) {
+    // many matrices, each too large for the shared memory of a few CTAs: small clusters working in L2, more in flight
+    G = batch_global;
+    cluster = true; smem_a = false;
   } else if (g_smem > 0 && g_smem <= 16 && (prefer_cluster || batch * g_smem > sms)) {
     // one thread-block cluster per matrix, scheduled by the hardware: batches that do not fit side by side, and the
     // middle phase of a single reduction (the cluster barrier is cheaper than the L2 counter exchange)
@@ -597,12 +605,17 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
     G = std::min(G, sms);
     smem_a = g_smem > 0 && G >= g_smem;
   }
-  const size_t smem = tf_smem_bytes(n, G, smem_a);
+  // columns in registers: <= 8 columns per CTA and <= 4 rows per thread (n = 1024 on 148 SMs)
+  static int rega_ok = -1;
+  if (rega_ok < 0) { const char* re = getenv("GSCF_B200_TF_REGA"); rega_ok = (re && re[0] == '0') ? 0 : 1; }
+  const bool rega = rega_ok && smem_a && !solo && !cluster && ceil_div(n, G) <= TF_RS && round_up(n, 2) <= 2 * 256 * TF_RP;
+  const size_t smem = tf_smem_bytes(n, G, smem_a && !rega);
   const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : (n <= 4096 ? 512 : 1024);
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
     if (solo) return tf_launch<1, true, 256, true>(a, G, cnt, false, smem, st);
+    if (rega) return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
     if (smem_a) {
       if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
@@ -615,7 +628,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   };
   const bool use_blocked = blocked && jstop == 0 && !smem_a && !cluster && G <= 256 && TFB_PW == 32 &&
                            n > tf_unblocked_below() && ceil_div(n, G) <= TF_MAXS;
-  if (cluster) {
+  if (cluster && smem_a) {
     int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
                     : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
     if (mc < 1) return -1;
