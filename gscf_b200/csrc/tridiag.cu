@@ -277,26 +277,32 @@ trd_finalize_w(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, i
 // (tau_r = 0, i.e. H_r = I, gives a zero row and column, as dlarft does).  The columns are independent: one quad
 // of threads per column, no block-wide barrier inside the recurrence.
 __global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __restrict__ map) {
+  // both triangles packed in shared memory (2 x 66 KB at NBQ = 128):
+  //   Xp: column c of T, entries k = 0..c, at c (c + 1) / 2          Gp: row r of G, entries k = r+1..pw-1, at gbase(r)
   extern __shared__ double sm[];
-  constexpr int LDT = NBQ + 1;
-  double* X = sm;                  // X[c*LDT + k] = T(k,c)
+  double* Xp = sm;
+  double* Gp = sm + NBQ * (NBQ + 1) / 2;
   __shared__ double stau[NBQ];
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
   const int b = blockIdx.x, j0 = b * NBQ, pw = min(NBQ, ws.n - 1 - j0);
-  // G is symmetric: row r is read as column r (contiguous in k), straight from L2 / L1
-  const double* __restrict__ Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw
+  const double* __restrict__ Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw, symmetric
+  auto gbase = [pw](int r) { return r * (2 * pw - r - 1) / 2 - (r + 1); };  // Gp[gbase(r) + k] = G(r, k), k > r
+  for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
+    const int k = idx / pw, r = idx - k * pw;  // element (r, k) of the column-major block
+    if (k > r) Gp[gbase(r) + k] = Gg[idx];
+  }
   for (int idx = threadIdx.x; idx < pw; idx += blockDim.x) stau[idx] = (ws.tau + q * ws.n + j0)[idx];
   __syncthreads();
   const int c = threadIdx.x >> 2, part = threadIdx.x & 3;
-  double* x = X + c * LDT;
+  double* x = Xp + c * (c + 1) / 2;
   const unsigned qmask = 0xFu << (threadIdx.x & 28);  // the four lanes of my quad: quads of a warp run different trip counts
   if (c < pw) {
     if (part == 0) x[c] = stau[c];
     __syncwarp(qmask);
     for (int r = c - 1; r >= 0; --r) {
-      const double* g = Gg + (size_t)r * pw;
+      const double* g = Gp + gbase(r);
       double s = 0.0;
-      for (int k = r + 1 + part; k <= c; k += 4) s = fma(__ldg(g + k), x[k], s);
+      for (int k = r + 1 + part; k <= c; k += 4) s = fma(g[k], x[k], s);
       s += __shfl_xor_sync(qmask, s, 1);
       s += __shfl_xor_sync(qmask, s, 2);
       if (part == 0) x[r] = -stau[r] * s;
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __r
   double* Tg = ws.Tall + (q * ws.nbq + b) * NBQ * NBQ;
   for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
     const int cc = idx / pw, r = idx - cc * pw;
-    Tg[idx] = r <= cc ? X[cc * LDT + r] : 0.0;
+    Tg[idx] = r <= cc ? Xp[cc * (cc + 1) / 2 + r] : 0.0;
   }
 }
 
@@ -879,7 +885,7 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
     GSCF_TRY(launch_gemm(true, false, gp, batch * nblocks, NBQ, NBQ, st));
   }
-  larft_kernel<<<dim3(nblocks, batch), 4 * NBQ, NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);
+  larft_kernel<<<dim3(nblocks, batch), 4 * NBQ, NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);  // two packed triangles
   bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 1, batch, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
