@@ -130,6 +130,67 @@ dgemm_dmma_kernel(const GemmParams p) {
     }
   };
 
+  // ---- TMA path: interior tiles of aligned operands are staged by bulk copies (one per contiguous tile row, into the
+  // same padded layout) that complete on one mbarrier per stage; edge tiles keep the predicated cp.async path
+  __shared__ __align__(8) uint64_t s_bar[STAGES];
+  // Only operands whose tile rows are long (m- or n-contiguous: BM / BN doubles = 0.5-1 KB per copy) go through TMA; a
+  // k-contiguous operand would need one 128-byte copy per row (measured: 13.8 instead of 28.4 TFLOP/s) and stays on cp.async.
+  const bool interior = p.use_tma && (m0 + BM <= m) && (n0 + BN <= n) && (k % BK == 0);
+  // ... and only when BOTH operands qualify (the NT products: F X^T, C_o C_o^T, the Pulay outer products, Q U^T of the
+  // D&C merges, L21 L21^T): mixing the two mechanisms in one stage measured slower than cp.async alone at n = 1024
+  // (18.8 vs 23.4 TFLOP/s), both through TMA faster (NT 4096^3: 30.0 vs 25.7 TFLOP/s).
+  const bool both = interior && !TA && TB && alignedA && alignedB;
+  const bool bulkA = both, bulkB = both;
+  const bool use_bulk = both;
+  if (use_bulk) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
+  auto load_tile_bulk = [&](int stage, int t) {
+    const int q = t / ktiles_per;
+    const int k0 = (t - q * ktiles_per) * BK;
+    double* sA = smem + stage * L::STAGE_ELEMS;
+    double* sB = sA + L::A_ELEMS;
+    const double* Aq = A + (size_t)q * p.skA;
+    const double* Bq = B + (size_t)q * p.skB;
+    const unsigned bytes = (unsigned)(((bulkA ? BM : 0) + (bulkB ? BN : 0)) * BK * sizeof(double));
+    // warp 0 issues the bulk copies: expect_tx first, then one copy per tile row
+    if (threadIdx.x < 32) {
+      fence_proxy_async();  // generic-proxy reads of this stage (ordered by the barrier above) before the async-proxy writes
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar[stage], bytes);
+      __syncwarp();
+      if (bulkA)
+        for (int r = threadIdx.x; r < L::A_SE; r += 32)
+          tma_bulk_g2s(sA + r * L::A_LD, Aq + (size_t)(k0 + r) * lda + m0, (unsigned)(L::A_CE * sizeof(double)), &s_bar[stage]);
+      if (bulkB)
+        for (int r = threadIdx.x; r < L::B_SE; r += 32)
+          tma_bulk_g2s(sB + r * L::B_LD, Bq + (size_t)(k0 + r) * ldb + n0, (unsigned)(L::B_CE * sizeof(double)), &s_bar[stage]);
+    }
+    // the other operand (k-contiguous rows) through cp.async
+    if (!bulkA) {
+      if (TA) {
+        if (alignedA) load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 2>(sA, Aq, lda, k0, m0, k, m);
+        else          load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 1>(sA, Aq, lda, k0, m0, k, m);
+      } else {
+        if (alignedA) load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 2>(sA, Aq, lda, m0, k0, m, k);
+        else          load_operand<L::A_CE, L::A_SE, L::A_LD, NT, 1>(sA, Aq, lda, m0, k0, m, k);
+      }
+    }
+    if (!bulkB) {
+      if (TB) {
+        if (alignedB) load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 2>(sB, Bq, ldb, n0, k0, n, k);
+        else          load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 1>(sB, Bq, ldb, n0, k0, n, k);
+      } else {
+        if (alignedB) load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 2>(sB, Bq, ldb, k0, n0, k, n);
+        else          load_operand<L::B_CE, L::B_SE, L::B_LD, NT, 1>(sB, Bq, ldb, k0, n0, k, n);
+      }
+    }
+  };
+
   double acc[MI][NI][2];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
@@ -138,17 +199,24 @@ dgemm_dmma_kernel(const GemmParams p) {
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (T0 + s < KT) load_tile(s, T0 + s);
+    if (T0 + s < KT) {
+      if (use_bulk) load_tile_bulk(s, T0 + s);
+      else load_tile(s, T0 + s);
+    }
     cp_async_commit();
   }
 
   for (int tt = 0; tt < KT - T0; ++tt) {
     const int t = tt;
     cp_async_wait<STAGES - 2>();
+    if (use_bulk) mbar_wait(&s_bar[t % STAGES], (unsigned)((t / STAGES) & 1));
     __syncthreads();
     {
       const int tn = t + STAGES - 1;
-      if (T0 + tn < KT) load_tile(tn % STAGES, T0 + tn);
+      if (T0 + tn < KT) {
+        if (use_bulk) load_tile_bulk(tn % STAGES, T0 + tn);
+        else load_tile(tn % STAGES, T0 + tn);
+      }
       cp_async_commit();
     }
     const double* sA = smem + (t % STAGES) * L::STAGE_ELEMS;
@@ -270,9 +338,13 @@ int launch_gemm_splitk(bool ta, bool tb, GemmParams p, int batch, int splits, do
   return GSCF_B200_OK;
 }
 
-int launch_gemm(bool ta, bool tb, const GemmParams& p, int batch, int max_m, int max_n,
+int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, int max_n,
                 cudaStream_t st) {
   if (batch <= 0 || max_m <= 0 || max_n <= 0) return GSCF_B200_OK;
+  static int tma = -1;
+  if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] == '0') ? 0 : 1; }
+  GemmParams p = pin;
+  p.use_tma = tma;
   if (batch > 65535) {
     set_last_error("gemm: batch > 65535 not supported in one launch");
     return GSCF_B200_ERR_INVALID_ARG;

@@ -36,6 +36,7 @@ struct GemmParams {
                           //   1: k < n0 + BN   (op(B)(k, j) = 0 for k > j)      2: k < m0 + BM   (op(A)(i, k) = 0 for k > i)
                           //   3: k >= m0       (op(A)(i, k) = 0 for k < i)
   int lower_only;         // 1: skip tiles strictly above the diagonal (symmetric result, mirrored by the caller)
+  int use_tma;            // stage interior tiles with TMA bulk copies (set by launch_gemm; GSCF_B200_GEMM_TMA=0 disables)
   int ksplit;             // > 1: split-k, blockIdx.z = entry * ksplit + split, partial tiles go to Cpart
   double* Cpart;          // [batch * ksplit][m * n] partial products (compact, ld = m)
 };
@@ -47,7 +48,7 @@ inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A
   p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
   p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
-  p.ksplit = 1; p.Cpart = nullptr; p.ktri = 0; p.lower_only = 0;
+  p.ksplit = 1; p.Cpart = nullptr; p.ktri = 0; p.lower_only = 0; p.use_tma = 0;
   return p;
 }
 
