@@ -281,3 +281,46 @@ def test_n_eigenpairs_partial(G):
     assert part["n_eigenpairs"] == k and full["n_eigenpairs"] == n
     with pytest.raises(Exception):
         _run_synthetic(G, n, o, aux, "diis", params={"n_eigenpairs": o - 1})
+
+
+def test_c2_full_size_parity(G):
+    """BASELINE configs[1] at full size (n_bf = 1024, n_occ = 128, n_aux = 64, DIIS 8) against the oracle: the parity gate
+    of north_star - same iteration count, |dE| <= 1e-10, max |d eps| <= 1e-9, ||dD||_F <= 1e-8."""
+    n, o, aux, m = 1024, 128, 64, 8
+    got = _run_synthetic(G, n, o, aux, "diis", params={"diis_n_prev_steps": m})
+    ref, p = _oracle_synthetic(n, o, aux, "diis", n_prev_steps=m)
+    assert got["n_iter"] == ref.n_iter
+    assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
+    assert np.abs(got["w"][0] - ref.orben[0]).max() < TOL_EPS
+    assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < TOL_D
+
+
+def test_c3_full_size_properties(G):
+    """BASELINE configs[2] at full size (n_bf = 4096, n_occ = 512; n_aux = 64 as in bench.py) through the blocked
+    tridiagonalisation: too large for the oracle inside a test, so the size-independent properties of a converged
+    closed-shell SCF are checked instead: C^T S C = I, D S D = D, tr(D S) = n_occ, F C = S C eps, [F, D]_S small."""
+    n, o, aux = 4096, 512, 64
+    fock = G.DeviceDFFock(n, o, None, n_aux=aux, seeds=[0])
+    eng, st = G.solve_device_problem(fock, "diis", {"diis_n_prev_steps": 10})
+    try:
+        from gscf_b200 import lib as L
+
+        assert st == L.OK, L.last_error()
+        assert int(eng.converged()[0]) == 1 and float(eng.error_norm()[0]) < 5e-7
+        C = eng.get_matrix("coeff")[0, 0]
+        D = eng.get_matrix("density")[0, 0]
+        F = eng.get_matrix("fock")[0, 0]
+        w = eng.orben()[0, 0]
+    finally:
+        eng.close()
+        fock.close()
+    from oracle.synthetic import SyntheticDFProblem
+
+    S = SyntheticDFProblem(n, o, n_aux=1, seed=0).S  # S and H do not depend on n_aux
+    assert np.all(np.diff(w) >= 0)
+    SC = S @ C
+    assert np.abs(C.T @ SC - np.eye(n)).max() < 1e-11
+    assert abs(np.trace(D @ S) - o) < 1e-9
+    assert np.linalg.norm(D @ S @ D - D) < 1e-10
+    assert np.abs(F @ C[:, :o] - SC[:, :o] * w[:o]).max() < 2e-6  # occupied block of the final Fock matrix: ~ the SCF error
+    assert np.linalg.norm(2.0 * (S @ D @ F - F @ D @ S)) < 5e-7
