@@ -61,6 +61,8 @@ __device__ __forceinline__ void tf_st2(double* p, double x, double y) {
   asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory");
 }
 // offset of entry r inside a step's chunked exchange slot (see the kernel)
+// release fence of the exchange: acq_rel at gpu scope (a `__threadfence()` is the stronger fence.sc)
+__device__ __forceinline__ void tf_fence_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned tf_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -154,6 +156,7 @@ trd_fused_kernel(const TfArgs a) {
 #ifdef GSCF_TF_DEBUG_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tbucket[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tfence = 0;
   long long tmark = clock64();
 #define TF_TICK(k) do { const long long _t = clock64(); tacc[k] += _t - tmark; tmark = _t; } while (0)
 #else
@@ -390,7 +393,13 @@ trd_fused_kernel(const TfArgs a) {
         cooperative_groups::this_cluster().sync();
       } else if (!SOLO) {
         if (tid == 0) {
-          __threadfence();
+#ifdef GSCF_TF_DEBUG_TIMING
+          const long long tf0 = clock64();
+#endif
+          tf_fence_release();
+#ifdef GSCF_TF_DEBUG_TIMING
+          tfence += clock64() - tf0;
+#endif
           atomicAdd(ctr, 1u);
           const unsigned target = (unsigned)G * (unsigned)(j + 1);
           if (*reinterpret_cast<volatile unsigned*>(a.abort_flag) == 0u) {
@@ -507,6 +516,7 @@ trd_fused_kernel(const TfArgs a) {
     printf("cta %d tid %d cycles/col: sweep %lld sync %lld publish %lld poll %lld dot %lld norm %lld vec %lld loop %lld\n", g, tid,
            tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
   if (tid == 0 && g == 0 && blockIdx.y == 0) {
+    printf("fence cycles/col %lld\n", tfence / n);
     printf("sweep cycles/col by sixteenth of the reduction:");
     for (int b = 0; b < 16; ++b) printf(" %lld", tbucket[b] * 16 / n);
     printf("\n");

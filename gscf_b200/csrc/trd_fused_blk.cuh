@@ -152,7 +152,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
         }
         __syncthreads();
         if (tid == 0) {
-          __threadfence();
+          tf_fence_release();
           atomicAdd(ctr2, 1u);
         }
         ++nA;
@@ -331,7 +331,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
       TFB_TICK(4);
       __syncthreads();
       if (tid == 0) {
-        __threadfence();
+        tf_fence_release();
         atomicAdd(ctr, 1u);
         wait_counter(ctr, (unsigned)G * (unsigned)(j + 1));
       }
