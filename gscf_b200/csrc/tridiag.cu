@@ -45,7 +45,9 @@ struct TrdWs {
   double* Gall;         // [cap][nbq][NBQ*NBQ]  V_b^T V_b
   double* Tall;         // [cap][nbq][NBQ*NBQ]  T_b
   GemmDesc* bdesc;      // [cap][nbq] descriptors of the per-block set-up GEMMs
-  int nbq;              // blocks of NBQ reflectors
+  int nbq;              // blocks of nbw reflectors
+  int nbw;              // block width of the back-transformation: 64 for n <= 256 (batches: small T factors, several
+                        // CTAs per SM in larft), NBQ = 128 above
   double* Yw;           // [cap][NBQ*n]
   int n, ld, nrb, ncb, cap;
 };
@@ -281,10 +283,11 @@ __global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __r
   //   Xp: column c of T, entries k = 0..c, at c (c + 1) / 2          Gp: row r of G, entries k = r+1..pw-1, at gbase(r)
   extern __shared__ double sm[];
   double* Xp = sm;
-  double* Gp = sm + NBQ * (NBQ + 1) / 2;
+  const int nbw = ws.nbw;
+  double* Gp = sm + nbw * (nbw + 1) / 2;
   __shared__ double stau[NBQ];
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
-  const int b = blockIdx.x, j0 = b * NBQ, pw = min(NBQ, ws.n - 1 - j0);
+  const int b = blockIdx.x, j0 = b * nbw, pw = min(nbw, ws.n - 1 - j0);
   const double* __restrict__ Gg = ws.Gall + (q * ws.nbq + b) * NBQ * NBQ;  // column-major, ld = pw, symmetric
   auto gbase = [pw](int r) { return r * (2 * pw - r - 1) / 2 - (r + 1); };  // Gp[gbase(r) + k] = G(r, k), k > r
   for (int idx = threadIdx.x; idx < pw * pw; idx += blockDim.x) {
@@ -364,7 +367,8 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
-  ws.nbq = std::max(1, ceil_div(n - 1, NBQ));
+  ws.nbw = n <= 256 ? 64 : NBQ;
+  ws.nbq = std::max(1, ceil_div(n - 1, ws.nbw));
   ws.Vf = cv.take<double>((size_t)cap * ld * n);
   ws.Wf = cv.take<double>((size_t)cap * ld * n);
   ws.Gall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
@@ -851,7 +855,7 @@ __global__ void bt_desc_kernel(TrdWs ws, int which, int batch, const int* __rest
   if (idx >= batch * ws.nbq) return;
   const int z = idx / ws.nbq, b = idx - z * ws.nbq;
   const long long q = map ? map[z] : z;
-  const int n = ws.n, j0 = b * NBQ, pw = min(NBQ, n - 1 - j0), m = n - j0 - 1;
+  const int n = ws.n, j0 = b * ws.nbw, pw = min(ws.nbw, n - 1 - j0), m = n - j0 - 1;
   const double* Vb = ws.Vf + q * (long long)ws.ld * n + (size_t)j0 * ws.ld + j0 + 1;
   GemmDesc d;
   if (which == 0) {
@@ -883,20 +887,20 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
   {
     GemmParams gp{};
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
-    GSCF_TRY(launch_gemm(true, false, gp, batch * nblocks, NBQ, NBQ, st));
+    GSCF_TRY(launch_gemm(true, false, gp, batch * nblocks, ws.nbw, ws.nbw, st));
   }
-  larft_kernel<<<dim3(nblocks, batch), 4 * NBQ, NBQ * (NBQ + 1) * sizeof(double), st>>>(ws, map);  // two packed triangles
+  larft_kernel<<<dim3(nblocks, batch), 4 * ws.nbw, (size_t)ws.nbw * (ws.nbw + 1) * sizeof(double), st>>>(ws, map);  // two packed triangles
   bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 1, batch, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   {
     GemmParams gp{};
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
-    GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, NBQ, st));
+    GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, ws.nbw, st));
   }
   for (int b = nblocks - 1; b >= 0; --b) {
-    const int j0 = b * NBQ;
-    const int pw = std::min(NBQ, nref - j0);
+    const int j0 = b * ws.nbw;
+    const int pw = std::min(ws.nbw, nref - j0);
     const int m = n - j0 - 1;  // rows j0+1 .. n-1
     const double* Vb = ws.Vf + (size_t)j0 * ws.ld + j0 + 1;
     const double* Wb = ws.Wf + (size_t)j0 * ws.ld + j0 + 1;
