@@ -5,6 +5,7 @@ include/gscf_b200.h).  This package is the Python host-side mirror of gscf's sol
 plugin interface; importing it fails loudly when the shared library has not been built.
 """
 from . import lib  # noqa: F401  (raises ImportError when libgscf_b200.so is missing)
+from . import observe  # noqa: F401
 from .solvers import (  # noqa: F401
     ALL,
     DeviceDFFock,

@@ -624,7 +624,12 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
-    if (solo) return tf_launch<1, true, 256, true>(a, G, cnt, false, smem, st);
+    if (solo) {
+      static int solo_t = -1;
+      if (solo_t < 0) { const char* se2 = getenv("GSCF_B200_TF_SOLO_T"); solo_t = se2 ? atoi(se2) : 256; }
+      if (solo_t == 512) return tf_launch<1, true, 512, true>(a, G, cnt, false, smem, st);
+      return tf_launch<1, true, 256, true>(a, G, cnt, false, smem, st);
+    }
     if (rega) return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
     if (smem_a) {
       if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);

@@ -589,6 +589,9 @@ class ScfBase:
                         state._engine = eng
                         if ev in (L.EV_UPDATE_PROBLEM_MATRIX, L.EV_AFTER_ITERATION):
                             self._mirror_scalars(eng, state)
+                        if self._method == "diis" and ev in (L.EV_NEW_DIAGMAT, L.EV_AFTER_ITERATION):
+                            c = eng.diis_coefficients()  # public state member, PulayDiisScf.hh:83-86
+                            state.diis_coefficients = c[0] if c.size else np.zeros(0)
                         getattr(self, hooks[ev])(state)
                         return 0
                     except Exception as exc:  # pragma: no cover

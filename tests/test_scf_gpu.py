@@ -324,3 +324,26 @@ def test_c3_full_size_properties(G):
     assert np.linalg.norm(D @ S @ D - D) < 1e-10
     assert np.abs(F @ C[:, :o] - SC[:, :o] * w[:o]).max() < 2e-6  # occupied block of the final Fock matrix: ~ the SCF error
     assert np.linalg.norm(2.0 * (S @ D @ F - F @ D @ S)) < 5e-7
+
+
+def test_verbose_scf_dump(G):
+    """examples/hartree_fock/ScfLibrary.hh:33-103 (VerboseScf) + the Mathematica dump of main.cc:49-54 through
+    gscf_b200.observe: every iteration prints / dumps eigenvalues, coefficients, the extrapolated matrix, the error norm."""
+    import io
+
+    from gscf_b200 import observe
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+
+    out, writer, rec = io.StringIO(), observe.MathematicaWriter(), observe.IterationRecorder()
+    cls = observe.verbose(G.PulayDiisScf, writer=writer, out=out, recorder=rec)
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    res = cls().solve(fock, fock.s_bb)
+    assert res.n_iter() == 6
+    text, dump = out.getvalue(), writer.getvalue()
+    assert text.count("Starting SCF iteration") == 6 and "E_total" in text
+    for it in range(1, 7):
+        assert f"evals{it} = {{" in dump and f"evecs{it} = {{{{" in dump and f"pulayerror{it} = " in dump
+    assert [r["iter"] for r in rec.records] == list(range(1, 7))
+    assert rec.records[-1]["error_norm"] < 5e-7
+    assert abs(rec.records[-1]["energy_total"] - res.energy_total) < 1e-12
+    assert len(rec.records[-1]["diis_coefficients"]) == 4  # ring of depth 4 is full from iteration 5 on
