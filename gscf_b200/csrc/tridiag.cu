@@ -624,6 +624,16 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
+    if (solo && n <= 128 && a.jstop == 0) {
+      static int solo_reg = -1;
+      if (solo_reg < 0) { const char* sr = getenv("GSCF_B200_TF_SOLO_REG"); solo_reg = (sr && sr[0] == '0') ? 0 : 1; }
+      if (solo_reg) {
+        trd_solo_reg_kernel<<<dim3(1, cnt), 256, 0, st>>>(a);
+        count_launch();
+        GSCF_CHECK_LAUNCH();
+        return GSCF_B200_OK;
+      }
+    }
     if (solo) {
       static int solo_t = -1;
       if (solo_t < 0) { const char* se2 = getenv("GSCF_B200_TF_SOLO_T"); solo_t = se2 ? atoi(se2) : 256; }

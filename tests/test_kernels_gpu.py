@@ -281,7 +281,9 @@ def test_syev_tridiag_dc_fock_like(env):
     (257, 3, {"GSCF_B200_TF_GLOBAL": "1", "GSCF_B200_TF_UNBLOCKED_BELOW": "100"}),  # blocked, odd order, switch-over
     (128, 40, {"GSCF_B200_TF_SOLO": "0"}),                                          # one cluster per matrix
     (512, 12, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # clusters with the L2 counter exchange
-    (130, 5, {}),                                                                   # one CTA per matrix (SOLO)
+    (130, 5, {}),                                                                   # one CTA per matrix (SOLO, shared memory)
+    (101, 6, {}),                                                                   # one CTA per matrix, registers
+    (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
     (1024, 2, {"GSCF_B200_TF_FUSED": "0"}),                                         # previous panel kernels still work
     (1024, 1, {"GSCF_B200_TF_PHASES": "1"}),                                        # all SMs -> 16-CTA cluster -> one CTA
     (700, 2, {"GSCF_B200_TF_PHASES": "1", "GSCF_B200_TF_PHASE_CLUSTER": "0"}),      # hand-over to the single-CTA tail
