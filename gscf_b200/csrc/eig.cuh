@@ -1,8 +1,8 @@
 // Symmetric eigensolvers (all eigenpairs, ascending) - the FLOP sink of ScfBase::update_eigenpairs
 // (ScfBase.hh:291-339).  Two hand-written paths, no cuSOLVER:
-//   * jacobi.cu   one CTA per matrix, one-sided cyclic Jacobi in shared memory   (n <= 160)
-//   * tridiag.cu + stedc.cu   blocked Householder tridiagonalisation, divide & conquer on the
-//                 tridiagonal matrix (DMMA GEMM merges), blocked back-transformation
+//   * jacobi.cu   one CTA per matrix, one-sided cyclic Jacobi in shared memory   (n <= 160; AUTO uses it for n <= 64)
+//   * tridiag.cu (+ trd_fused*.cuh) + stedc.cu   fused one-launch Householder tridiagonalisation, divide & conquer on
+//                 the tridiagonal matrix (DMMA GEMM merges), blocked back-transformation
 #pragma once
 #include "common.cuh"
 

@@ -4,14 +4,15 @@
 //
 // The tree is balanced: 2^L leaves with boundaries bnd(i) = floor(i n / 2^L); all merges of a
 // level have (almost) the same size and run in the same launches.  Per level:
-//   dc_prepare   one CTA per merge: z vector, sort, deflation (dc_core.hpp, in shared memory),
-//                column typing, Givens rotations of near-degenerate pairs
-//   dc_secular   one thread per root of the secular equation; writes delta(j,i) = d_j - lam_i
+//   dc_prepare   one CTA per merge: z vector, rank sort, deflation (parallel block scans; the sequential dlaed2 logic
+//                of dc_core.hpp only when a pair needs a Givens rotation), column typing, the rotations
+//   dc_secular   one warp per root of the secular equation; writes delta(j,i) = d_j - lam_i
 //   dc_zhat      one warp per pole: Gu-Eisenstat recomputation of z
 //   dc_vectors   eigenvectors of the rank-one problem, rows grouped by column type
 //   dc_gather    non-deflated columns -> Gq, deflated columns/eigenvalues -> output; GEMM descriptors
 //   grouped DMMA GEMM  Q_top * U_top and Q_bot * U_bot with device-side sizes (after deflation)
-// Leaves are solved by the shared-memory Jacobi kernel (jacobi.cu).
+// Leaves (order <= 32 in batches, <= 16 for a few large matrices) are solved by dc_leaf_tql2_kernel: implicit QL
+// iteration, one warp per leaf.
 #include "stedc.cuh"
 
 #include "dc_core.hpp"

@@ -1,17 +1,21 @@
-// Large-n symmetric eigensolver: blocked Householder tridiagonalisation, divide & conquer on the
-// tridiagonal matrix (stedc.cu), blocked back-transformation.  Batched over matrices.
+// Symmetric eigensolver above the Jacobi range: Householder tridiagonalisation, divide & conquer on the tridiagonal
+// matrix (stedc.cu), blocked back-transformation.  Batched over matrices.
 //
 //   A = Q T Q^T   (Q = H(0) H(1) ... H(n-2), H(i) = I - tau_i v_i v_i^T, LAPACK dsytrd "lower")
 //   T = Z_T diag(w) Z_T^T     (stedc.cu)
 //   Z = Q Z_T                 (compact-WY block reflectors, DMMA GEMMs)
 //
-// Tridiagonalisation: panels of NB columns; inside a panel every column needs one product with
-// the trailing matrix (HBM/L2-bound, 8 (n-i)^2 bytes per column on the full symmetric storage)
-// and the rank-2 updates are deferred to one pair of DMMA GEMMs per panel (dlatrd scheme).  Per
-// column three launches whose boundaries are the global dependencies of the algorithm:
-//   trd_col_update : a_i <- A(:,i) - V W(i,:)^T - W V(i,:)^T, partial |a_i|^2       (needs w_{i-1})
-//   trd_symv       : y = A22 v_i in 128x128 tiles + partial V^T v, W^T v              (needs v_i)
-//   trd_assemble_w : w_i = tau (y - V (W^T v) - W (V^T v)), partial w^T v             (needs y)
+// Tridiagonalisation - the production path is the fused one-launch reduction of trd_fused.cuh / trd_fused_blk.cuh
+// (tridiagonalise_fused below picks the variant: single CTA in registers or shared memory, cluster per matrix,
+// cooperative group with the columns in registers / shared memory / L2, blocked for matrices larger than L2).
+// The older panel schemes are kept as fall-backs (GSCF_B200_TRD_FUSED=0, exercised by the variant tests):
+//   legacy (GSCF_B200_TRD_LEGACY=1): three launches per column at the global dependencies of dlatrd,
+//     trd_col_update : a_i <- A(:,i) - V W(i,:)^T - W V(i,:)^T, partial |a_i|^2       (needs w_{i-1})
+//     trd_symv       : y = A22 v_i in 128x128 tiles + partial V^T v, W^T v              (needs v_i)
+//     trd_assemble_w : w_i = tau (y - V (W^T v) - W (V^T v)), partial w^T v             (needs y)
+//   trd_panel.cuh  : the same three steps as group barriers inside one cooperative launch per panel,
+//   trd_cluster.cuh: ... inside one thread-block cluster with DSMEM exchange,
+//   each followed by the deferred rank-2k DMMA GEMM update of the trailing matrix.
 #include "eig.cuh"
 #include "gemm.cuh"
 #include "stedc.cuh"
