@@ -17,6 +17,11 @@ namespace gscfb {
 
 constexpr int kJacobiMaxSweeps = 40;
 
+__device__ __forceinline__ long long sort_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return b < 0 ? (b ^ 0x7fffffffffffffffLL) : b;
+}
+
 template <int NPL, int PPW>
 __global__ void __launch_bounds__(1024)
 jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long strideA,
@@ -183,16 +188,21 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
     if (lane == 0) lam[c] = nrm - sigma;
   }
   __syncthreads();
+  // garbage in (NaN / Inf) must be reported, not sorted into a plausible-looking spectrum
+  int bad = 0;
+  for (int c = tid; c < n; c += nthr) bad |= isfinite(lam[c]) ? 0 : 1;
+  bad = __syncthreads_or(bad);
 
   // ---- rank sort ascending (ties broken by index) and scatter to global ------------------------
   double* wout = w + prob * stride_w;
   double* Zout = Z + prob * strideZ;
   for (int c = warp; c < n; c += nwarp) {
     const double lc = lam[c];
+    const long long kc = sort_key(lc);
     int rank = 0;
     for (int j = lane; j < n; j += 32) {
-      const double lj = lam[j];
-      rank += (lj < lc || (lj == lc && j < c)) ? 1 : 0;
+      const long long kj = sort_key(lam[j]);  // total order on the bit patterns: a permutation even with NaNs
+      rank += (kj < kc || (kj == kc && j < c)) ? 1 : 0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
@@ -200,7 +210,7 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
     const double* g = G + (size_t)c * ldg;
     for (int r = lane; r < n; r += 32) Zout[(size_t)rank * ldz + r] = g[r];
   }
-  if (tid == 0 && info) info[prob] = converged ? 0 : 1;
+  if (tid == 0 && info) info[prob] = (converged && !bad) ? 0 : 1;
 }
 
 size_t jacobi_smem_bytes(int n) {

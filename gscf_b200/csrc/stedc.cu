@@ -26,6 +26,14 @@ constexpr int kLeaf = 32;  // maximum leaf order
 
 __host__ __device__ inline int bnd(int i, int n, int L) { return (int)(((long long)i * n) >> L); }
 
+// Total order on doubles for the rank sorts (-NaN < -inf < ... < +inf < +NaN; -0 < +0): with a plain `<` a NaN in the
+// spectrum (garbage input) would give two entries the same rank, leave a slot of the permutation unwritten and send
+// the gather out of bounds.  For ordinary numbers the order is the usual one.
+__device__ __forceinline__ long long dc_sort_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return b < 0 ? (b ^ 0x7fffffffffffffffLL) : b;
+}
+
 struct NodeGeom {
   int lo, mid, hi;
 };
@@ -242,10 +250,10 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
   __syncthreads();
   // rank sort (ties by index) -> idx
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const double dj = sd[j];
+    const long long dj = dc_sort_key(sd[j]);
     int r = 0;
     for (int i = 0; i < k; ++i) {
-      const double di = sd[i];
+      const long long di = dc_sort_key(sd[i]);
       r += (di < dj || (di == dj && i < j)) ? 1 : 0;
     }
     sidx[r] = j;
@@ -527,10 +535,10 @@ __global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, cons
   const double* lam = ws.lam[lev] + q * n;
   int* rank = ws.rank + q * n;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const double lj = lam[j];
+    const long long lj = dc_sort_key(lam[j]);
     int r = 0;
     for (int i = 0; i < n; ++i) {
-      const double li = lam[i];
+      const long long li = dc_sort_key(lam[i]);
       r += (li < lj || (li == lj && i < j)) ? 1 : 0;
     }
     rank[j] = r;

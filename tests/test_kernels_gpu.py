@@ -300,3 +300,35 @@ def test_syev_fused_variants(env, n, batch, envs):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "syev_variant_main.py"), str(n), str(batch)],
                        cwd=root, env=child_env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("n,method", [(40, 1), (100, 2), (300, 2), (1024, 2)])
+def test_syev_nan_input_is_contained(env, n, method):
+    """Garbage in one matrix of a batch (a NaN entry) must neither hang a spinning kernel nor send an index-building
+    kernel out of bounds (the D&C rank sorts use a total order on the bit patterns); the matrix is flagged through
+    info or non-finite eigenvalues and its neighbours in the batch are still solved correctly."""
+    torch, L = env
+    rng = np.random.default_rng(n)
+    batch = 1 if n > 512 else 3
+    ld = L.lib.gscf_b200_padded_ld(n)
+    a = rng.standard_normal((n, n))
+    a = a + a.T
+    buf = np.zeros((batch, n, ld))
+    buf[:, :, :n] = a
+    buf[0, 5, 7] = buf[0, 7, 5] = np.nan
+    dA = dev(torch, buf.ravel())
+    dw = torch.zeros(batch * n, dtype=torch.float64, device="cuda")
+    dZ = torch.zeros(batch * ld * n, dtype=torch.float64, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    wsz = L.lib.gscf_b200_syev_worksize(n, batch, method)
+    work = torch.zeros(max(1, wsz // 8 + 1), dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_syev(method, n, dA.data_ptr(), ld, ld * n, dw.data_ptr(), n, dZ.data_ptr(), ld, ld * n,
+                                 batch, work.data_ptr(), wsz, info.data_ptr(), None))
+    torch.cuda.synchronize()  # an illegal address would surface here
+    w = dw.cpu().numpy().reshape(batch, n)
+    flags = info.cpu().numpy()
+    assert flags[0] != 0 or not np.isfinite(w[0]).all()
+    wref = np.linalg.eigvalsh(a)
+    for b in range(1, batch):
+        assert flags[b] == 0
+        assert np.abs(w[b] - wref).max() < 1e-12 * n * max(1.0, np.abs(wref).max())
