@@ -347,3 +347,41 @@ def test_verbose_scf_dump(G):
     assert rec.records[-1]["error_norm"] < 5e-7
     assert abs(rec.records[-1]["energy_total"] - res.energy_total) < 1e-12
     assert len(rec.records[-1]["diis_coefficients"]) == 4  # ring of depth 4 is full from iteration 5 on
+
+
+def test_error_paths_overlap_and_nan_fock(G):
+    """Failure detection: an overlap that is not positive definite is refused at set-up
+    (ERR_INVALID_ARG), a problem matrix with a NaN fails the inner eigensolver (ExcInnerEigensolverFailed,
+    ScfBase.hh:33-36,335) - neither crashes nor hangs the device, and the engine stays usable afterwards."""
+    from gscf_b200 import lib as L
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+
+    n = 96
+    rng = np.random.default_rng(3)
+    S_bad = np.eye(n)
+    S_bad[3, 3] = -1.0
+    eng = G.Engine(n, 12)
+    try:
+        buf = np.ascontiguousarray(S_bad.T).ravel()
+        st = L.lib.gscf_b200_set_overlap(eng.handle, buf.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)), n, L.HOST)
+        assert st == L.ERR_INVALID_ARG and "positive definite" in L.last_error()
+        # the same engine accepts a valid overlap afterwards
+        S_ok = np.eye(n) + 0.01 * (lambda a: a + a.T)(rng.standard_normal((n, n)))
+        buf = np.ascontiguousarray(S_ok.T).ravel()
+        st = L.lib.gscf_b200_set_overlap(eng.handle, buf.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)), n, L.HOST)
+        assert st == L.OK, L.last_error()
+    finally:
+        eng.close()
+
+    class NanFock(Sturmian14Fock):
+        def as_dense(self):
+            F = np.array(super().as_dense(), dtype=float)
+            F[2, 3] = F[3, 2] = np.nan
+            return F
+
+    fock = NanFock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    with pytest.raises((G.ExcInnerEigensolverFailed, L.GscfB200Error)):
+        G.PlainScf().solve(fock, fock.s_bb)
+    # and a healthy solve still works in the same process
+    good = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    assert G.PlainScf().solve(good, good.s_bb).n_iter() == 12
