@@ -893,11 +893,11 @@ __global__ void bt_desc_kernel(TrdWs ws, int which, int batch, const int* __rest
 // Z <- Q Z with the reflectors stored in A / tau:  Q = H(0) .. H(n-2) = prod_b (I - V_b T_b V_b^T).
 // Everything that does not depend on Z is done up front for all blocks at once (V, G_b, T_b, W_b = V_b T_b: four
 // launches); the sequential part is two GEMMs per block:  Y = V_b^T Z,  Z -= W_b Y.
-int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& ws, double* Z, int ldz,
-                   long long sZ, int batch, const int* map, cudaStream_t st, int nvec) {
+// Z-independent part: V (explicit), G_b = V_b^T V_b, T_b, W_b = V_b T_b for all blocks.  Depends only on the
+// tridiagonalisation, so the caller runs it on a side stream while the divide & conquer stage occupies the main one.
+int back_transform_setup(int n, const double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
+                         cudaStream_t st) {
   if (n < 2) return GSCF_B200_OK;
-  const int nz = (nvec > 0 && nvec < n) ? nvec : n;  // columns of Z that are wanted
-  const int nref = n - 1;  // reflectors 0..n-2
   const int nblocks = ws.nbq;
   extract_v_all_kernel<<<dim3(std::max(1, std::min(8, ceil_div(n, 256))), n, batch), 256, 0, st>>>(A, lda, sA, ws, map);
   bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 0, batch, map);
@@ -917,6 +917,15 @@ int back_transform(int n, const double* A, int lda, long long sA, const TrdWs& w
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
     GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, ws.nbw, st));
   }
+  return GSCF_B200_OK;
+}
+
+int back_transform(int n, const TrdWs& ws, double* Z, int ldz, long long sZ, int batch, const int* map, cudaStream_t st,
+                   int nvec) {
+  if (n < 2) return GSCF_B200_OK;
+  const int nz = (nvec > 0 && nvec < n) ? nvec : n;  // columns of Z that are wanted
+  const int nref = n - 1;  // reflectors 0..n-2
+  const int nblocks = ws.nbq;
   for (int b = nblocks - 1; b >= 0; --b) {
     const int j0 = b * ws.nbw;
     const int pw = std::min(ws.nbw, nref - j0);
@@ -974,11 +983,34 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   phase_mark(PH_TRIDIAG, true, st);
   GSCF_TRY(tridiagonalise(n, A, lda, strideA, ws, batch, batch_map, st));
   phase_mark(PH_TRIDIAG, false, st);
+  // fork: the block factors of the back-transformation on a side stream, concurrently with the D&C stage
+  // per host thread: engines on distinct streams may be driven from distinct threads
+  static thread_local cudaStream_t side = nullptr;
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static thread_local int overlap = -1;
+  if (overlap < 0) {
+    const char* oe = getenv("GSCF_B200_BT_OVERLAP");
+    overlap = (oe && oe[0] == '0') ? 0 : 1;
+    if (overlap && (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+      cudaGetLastError();
+      overlap = 0;
+    }
+  }
+  if (overlap) {
+    GSCF_CUDA_TRY(cudaEventRecord(ev_fork, st));
+    GSCF_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+    GSCF_TRY(back_transform_setup(n, A, lda, strideA, ws, batch, batch_map, side));
+    GSCF_CUDA_TRY(cudaEventRecord(ev_join, side));
+  }
   phase_mark(PH_STEDC, true, st);
   GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st));
   phase_mark(PH_STEDC, false, st);
   phase_mark(PH_BACKTRANSFORM, true, st);
-  GSCF_TRY(back_transform(n, A, lda, strideA, ws, Z, ldz, strideZ, batch, batch_map, st, nvec));
+  if (overlap) GSCF_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
+  else GSCF_TRY(back_transform_setup(n, A, lda, strideA, ws, batch, batch_map, st));
+  GSCF_TRY(back_transform(n, ws, Z, ldz, strideZ, batch, batch_map, st, nvec));
   phase_mark(PH_BACKTRANSFORM, false, st);
   return GSCF_B200_OK;
 }
