@@ -237,6 +237,7 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
     sd = ws.dwork + q * n + lo; sz = ws.z + q * n + lo; sdl = ws.dlamda + q * n + lo; sw = ws.w + q * n + lo;
     sidx = ws.idx + q * n + lo; sct = ws.ctype + q * n + lo; snd = ws.ndcol + q * n + lo; sdc = ws.dcol + q * n + lo;
   }
+  long long* skey = reinterpret_cast<long long*>(sw);  // sort keys; sw (pole weights) is only written by the deflation
   const double ecoup = (e + q * dstride)[g.mid - 1];
   const double sgn = ecoup < 0.0 ? -1.0 : 1.0;
   const double rho = 2.0 * fabs(ecoup);
@@ -246,14 +247,15 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
     const double zz = j < n1 ? Zq[(size_t)(lo + j) * ldin + (g.mid - 1)] : sgn * Zq[(size_t)(lo + j) * ldin + g.mid];
     sz[j] = zz * rs2;
     sct[j] = j < n1 ? 1 : 3;
+    skey[j] = dc_sort_key(lam_in[j]);
   }
   __syncthreads();
   // rank sort (ties by index) -> idx
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const long long dj = dc_sort_key(sd[j]);
+    const long long dj = skey[j];
     int r = 0;
     for (int i = 0; i < k; ++i) {
-      const long long di = dc_sort_key(sd[i]);
+      const long long di = skey[i];
       r += (di < dj || (di == dj && i < j)) ? 1 : 0;
     }
     sidx[r] = j;
