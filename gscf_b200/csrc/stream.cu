@@ -45,6 +45,37 @@ multidot_partial_kernel(const double* __restrict__ e_new, long long pstride_new,
   double acc[COUNT_MAX];
 #pragma unroll
   for (int j = 0; j < COUNT_MAX; ++j) acc[j] = 0.0;
+  if (vec_ok && rows == ld) {
+    // no padding rows: the matrices are flat arrays of double2.  Every CTA streams one contiguous chunk of each
+    // operand (DRAM page locality), two items per thread and pass = 2 (count + 1) independent 16-byte loads in flight
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = min(total, lo + per);
+    const double2* en2 = reinterpret_cast<const double2*>(en);
+    for (long long w = lo + threadIdx.x; w < hi; w += 2 * blockDim.x) {
+      const long long w1 = w + blockDim.x;
+      const bool has1 = w1 < hi;
+      const double2 xa = en2[w];
+      const double2 xb = has1 ? en2[w1] : make_double2(0.0, 0.0);
+      double2 ya[COUNT_MAX], yb[COUNT_MAX];
+#pragma unroll
+      for (int j = 0; j < COUNT_MAX; ++j) {
+        if (j < slots.n) {
+          const double2* q = reinterpret_cast<const double2*>(rg + (size_t)slots.slot[j] * slot_stride);
+          ya[j] = q[w];
+          yb[j] = has1 ? q[w1] : make_double2(0.0, 0.0);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < COUNT_MAX; ++j) {
+        if (j < slots.n) {
+          acc[j] = fma(xa.x, ya[j].x, acc[j]);
+          acc[j] = fma(xa.y, ya[j].y, acc[j]);
+          acc[j] = fma(xb.x, yb[j].x, acc[j]);
+          acc[j] = fma(xb.y, yb[j].y, acc[j]);
+        }
+      }
+    }
+  } else
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
        w += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(w / pairs);
@@ -76,26 +107,35 @@ multidot_partial_kernel(const double* __restrict__ e_new, long long pstride_new,
       }
     }
   }
+  // per-warp sums into shared memory, one barrier, then thread j adds the warps in order (deterministic)
+  __shared__ double swarp[kStreamThreads / 32][COUNT_MAX];
+  (void)red;
 #pragma unroll
   for (int j = 0; j < COUNT_MAX; ++j) {
-    if (j < slots.n) {
-      const double s = block_sum(acc[j], red);
-      if (threadIdx.x == 0)
-        partial[((size_t)z * gridDim.x + blockIdx.x) * kMaxHistory + j] = s;
-    }
+    const double s = warp_sum(acc[j]);
+    if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < slots.n) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kStreamThreads / 32; ++w) s += swarp[w][threadIdx.x];
+    partial[((size_t)z * gridDim.x + blockIdx.x) * kMaxHistory + threadIdx.x] = s;
   }
 }
 
 __global__ void multidot_final_kernel(const double* __restrict__ partial, int nblocks, int count,
                                       const int* __restrict__ batch_map, double* __restrict__ out,
                                       int out_stride) {
+  // one warp per dot product: lane l adds blocks l, l + 32, ... in order, then a butterfly (fixed order: deterministic)
   const int z = blockIdx.x;
-  const int j = threadIdx.x;
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (j >= count) return;
   const long long p = batch_map ? batch_map[z] : z;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[((size_t)z * nblocks + b) * kMaxHistory + j];
-  out[p * out_stride + j] = s;
+  for (int b = lane; b < nblocks; b += 32) s += partial[((size_t)z * nblocks + b) * kMaxHistory + j];
+  s = warp_sum(s);
+  if (lane == 0) out[p * out_stride + j] = s;
 }
 
 size_t multidot_worksize(int count, int rows, int cols, int batch) {
@@ -123,7 +163,7 @@ int multidot(const double* e_new, long long pstride_new, const double* ring, lon
         e_new, pstride_new, ring, slot_stride, pstride_ring, slots, rows, cols, ld, batch_map, work);
   count_launch();
   GSCF_CHECK_LAUNCH();
-  multidot_final_kernel<<<batch, 32, 0, st>>>(work, blocks, slots.n, batch_map, out_dev, out_stride);
+  multidot_final_kernel<<<batch, 32 * slots.n, 0, st>>>(work, blocks, slots.n, batch_map, out_dev, out_stride);
   count_launch();
   GSCF_CHECK_LAUNCH();
   return GSCF_B200_OK;
@@ -149,6 +189,37 @@ axpby_n_kernel(double* __restrict__ out, long long pstride_out, const double* __
   const long long total = (long long)pairs * cols;
   const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(rg) & 15) == 0) && ((slot_stride & 1) == 0);
+  if (vec_ok && rows == ld) {
+    // flat double2 arrays, one contiguous chunk per CTA, two items per thread and pass (see multidot)
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per, hi = min(total, lo + per);
+    double2* o2 = reinterpret_cast<double2*>(o);
+    for (long long w = lo + threadIdx.x; w < hi; w += 2 * blockDim.x) {
+      const long long w1 = w + blockDim.x;
+      const bool has1 = w1 < hi;
+      double2 ya[COUNT_MAX], yb[COUNT_MAX];
+#pragma unroll
+      for (int j = 0; j < COUNT_MAX; ++j) {
+        if (j < slots.n) {
+          const double2* q = reinterpret_cast<const double2*>(rg + (size_t)slots.slot[j] * slot_stride);
+          ya[j] = q[w];
+          yb[j] = has1 ? q[w1] : make_double2(0.0, 0.0);
+        }
+      }
+      double2 sa = make_double2(0.0, 0.0), sb = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < COUNT_MAX; ++j) {
+        if (j < slots.n) {  // same left-to-right order as the general path below
+          sa.x = (j == 0) ? cf[0] * ya[0].x : fma(cf[j], ya[j].x, sa.x);
+          sa.y = (j == 0) ? cf[0] * ya[0].y : fma(cf[j], ya[j].y, sa.y);
+          sb.x = (j == 0) ? cf[0] * yb[0].x : fma(cf[j], yb[j].x, sb.x);
+          sb.y = (j == 0) ? cf[0] * yb[0].y : fma(cf[j], yb[j].y, sb.y);
+        }
+      }
+      o2[w] = sa;
+      if (has1) o2[w1] = sb;
+    }
+  } else
   for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < total;
        w += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(w / pairs);
