@@ -386,7 +386,10 @@ trd_fused_kernel(const TfArgs a) {
       }
       // ================= exchange: arrive, wait for the other CTAs, load y and the raw column =================
       TF_TICK(2);
-      __syncthreads();  // the y stores above and the raw stores of the sweep are ordered before the fence below
+      // the y stores above (threads 0 .. S-s0-1) and the raw stores of the sweep (ordered by the barrier after the sweep)
+      // must precede the release fence of thread 0: a warp barrier is enough while the y writers share its warp
+      if (S <= 32) __syncwarp();
+      else __syncthreads();
       if (!SOLO && a.cluster) {
         // barrier.cluster.arrive.release / wait.acquire: the y and raw stores of every CTA of the cluster are visible
         // to all of them afterwards; no L2 atomic, no polling
