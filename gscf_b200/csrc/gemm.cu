@@ -301,7 +301,10 @@ template <bool TA, bool TB>
 static int launch_t(const GemmParams& p, int batch, int max_m, int max_n, cudaStream_t st) {
   // Large tiles once the grid still covers the 148 SMs; small tiles otherwise.
   const long long big_tiles = (long long)ceil_div(max_m, 128) * ceil_div(max_n, 128) * batch;
-  if (big_tiles >= 120)
+  // ... unless they would be mostly padding (batches of 64-wide panels: 128 x 128 tiles half empty)
+  const double fill128 = (double)max_m * max_n / ((double)ceil_div(max_m, 128) * ceil_div(max_n, 128) * 128.0 * 128.0);
+  const double fill64 = (double)max_m * max_n / ((double)ceil_div(max_m, 64) * ceil_div(max_n, 64) * 64.0 * 64.0);
+  if (big_tiles >= 120 && !(fill128 < 0.7 && fill64 > fill128 * 1.3))
     return launch_cfg<128, 128, 16, 64, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
   return launch_cfg<64, 64, 16, 32, 32, 3, TA, TB>(p, batch, max_m, max_n, st);
 }
