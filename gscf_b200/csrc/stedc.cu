@@ -467,10 +467,12 @@ dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   double* U = ws.U + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
   const double* zh = ws.zhat + q * n + lo;
   const int* gpos = ws.gpos + q * n + lo;
+  // pass 1: unnormalised components (one division each) into U, norms; pass 2: scale in place (same thread, same entries)
   double nrm = 0.0;
   if (i < K)
     for (int j = warp; j < K; j += 8) {
       const double u = zh[j] / S[(size_t)j * ws.ld + i];
+      U[(size_t)gpos[j] * ws.ld + i] = u;
       nrm = fma(u, u, nrm);
     }
   snrm[warp][lane] = nrm;
@@ -480,7 +482,7 @@ dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   for (int w = 0; w < 8; ++w) tot += snrm[w][lane];
   const double inv = 1.0 / sqrt(tot);
   if (i < K)
-    for (int j = warp; j < K; j += 8) U[(size_t)gpos[j] * ws.ld + i] = zh[j] / S[(size_t)j * ws.ld + i] * inv;
+    for (int j = warp; j < K; j += 8) U[(size_t)gpos[j] * ws.ld + i] *= inv;
 }
 
 // Gather non-deflated columns (grouped by type) into Gq, copy deflated columns/eigenvalues to the
