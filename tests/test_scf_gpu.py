@@ -385,3 +385,30 @@ def test_error_paths_overlap_and_nan_fock(G):
     # and a healthy solve still works in the same process
     good = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
     assert G.PlainScf().solve(good, good.s_bb).n_iter() == 12
+
+
+def test_chained_diis_then_toda_with_guess(G):
+    """BASELINE configs[2] runs "DIIS ... then TruncatedOptDampScf": the hand-over is solve_with_guess
+    (ScfBase.hh:152-180, ScfStateBase.hh:192-212,291-303) - eigensolution copied, F rebuilt once, DIIS history NOT
+    transferred.  Same chain through the oracle: iteration counts of both legs and the final energy must agree."""
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+    from oracle import pulay_diis_scf, truncated_opt_damp_scf
+    from oracle.mock_fock import IntegralsSturmian14, MockFockProblem
+
+    loose, tight = 1e-3, 5e-7
+    # oracle chain
+    prob = MockFockProblem(IntegralsSturmian14(4.0, GOLD["k_exp"]), 2, 2)
+    F0, e1, e2 = prob.fock(functionality_guess())
+    o1 = pulay_diis_scf(prob, F0, e1, e2, n_prev_steps=4, max_error_norm=loose)
+    F1, e1b, e2b = prob.fock(o1.C[0])
+    o2 = truncated_opt_damp_scf(prob, F1, e1b, e2b, max_error_norm=tight)
+    # GPU chain
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    s1 = G.PulayDiisScf({"max_error_norm": loose}).solve(fock, fock.s_bb)
+    fock2 = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    s2 = G.TruncatedOptDampScf({"max_error_norm": tight}).solve_with_guess(fock2, fock2.s_bb, s1)
+    assert s1.n_iter() == o1.n_iter and s2.n_iter() == o2.n_iter
+    assert s2.last_error_norm < tight
+    assert abs(s2.energy_total - o2.energy_total) < TOL_E
+    assert abs(s2.energy_total - GOLD["exp_energy_total"]) < GOLD["basetol"]
+    assert fock2.n_updates == s2.n_iter() + 1  # one rebuild from the guess, one per iteration
