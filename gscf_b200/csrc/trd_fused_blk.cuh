@@ -107,7 +107,9 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
 #else
 #define TFB_TICK(k) do { } while (0)
 #endif
-  for (int j = -1; j <= n - 2; ++j) {
+  // jstop (see trd_fused.cuh): only honoured in the unblocked regime, where exactly one reflector is pending
+  const int jlast = (a.jstop > 0 && a.jstop <= n - 2 && n - a.jstop < a_unblocked_below) ? a.jstop - 1 : n - 2;
+  for (int j = -1; j <= jlast; ++j) {
     const int first = j + 1;
     double yv[KMAX], rv[KMAX];
     TFB_TICK(7);
@@ -410,6 +412,17 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
     TFB_TICK(6);
     double* t = svc; svc = svn; svn = t;
     tau_j = tau_n;
+  }
+  if (jlast < n - 2) {
+    // hand-over: apply the pending reflector jstop-1 (svn = v, sw = w after the last swap) to my columns >= jstop in place
+    const int js = a.jstop;
+    const int s0 = js > g ? (js - g + G - 1) / G : 0;
+    for (int slot = s0; slot < S; ++slot) {
+      const int c = g + slot * G;
+      const double wc = sw[c], vc = svn[c];
+      double* col = A + (size_t)c * lda;
+      for (int r = js + tid; r < n; r += T) col[r] = fma(-svn[r], wc, fma(-sw[r], vc, col[r]));
+    }
   }
 #ifdef GSCF_TF_DEBUG_TIMING
   if ((tid == 0 || tid == T - 1) && (g == 0 || g == G - 1) && blockIdx.y == 0)

@@ -655,8 +655,8 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
     if (T == 512) return tf_launch<8, false, 512>(a, G, cnt, cluster, smem, st);
     return tf_launch<8, false, 1024>(a, G, cnt, cluster, smem, st);
   };
-  const bool use_blocked = blocked && jstop == 0 && !smem_a && !cluster && G <= 256 && TFB_PW == 32 &&
-                           n > tf_unblocked_below() && ceil_div(n, G) <= TF_MAXS;
+  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below() &&
+                           ceil_div(n, G) <= TF_MAXS && (jstop == 0 || n - jstop < tf_unblocked_below());
   if (cluster && smem_a) {
     int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
                     : (K <= 4 ? tf_max_clusters<4, true, 256>(G, smem) : tf_max_clusters<8, true, 256>(G, smem));
@@ -691,7 +691,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
 // Returns -1 when the fused kernels do not cover the case (caller falls back to the panel kernels).
 int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                          cudaStream_t st) {
-  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144;
+  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144, handover_on = 1, t_smem = 1664;
   if (enabled < 0) {
     const char* env = getenv("GSCF_B200_TRD_FUSED");
     enabled = (env && env[0] == '0') ? 0 : 1;
@@ -709,6 +709,8 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     if (tc) t_cluster = atoi(tc) & ~1;
     const char* ts = getenv("GSCF_B200_TF_PHASE_SOLO");
     if (ts) t_solo = atoi(ts) & ~1;
+    const char* he = getenv("GSCF_B200_TF_HANDOVER");
+    if (he) { handover_on = atoi(he) > 0 ? 1 : 0; if (atoi(he) > 1) t_smem = atoi(he) & ~1; }
   }
   if (!enabled || n < 3 || (lda & 1) || n > 8192) return -1;
   GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, ((size_t)4 * ws.cap + 1) * sizeof(unsigned), st));
@@ -717,13 +719,15 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   while (true) {
     const int ns = n - off;
     int jstop = 0;
-    // the blocked kernel (orders above tf_unblocked_below()) runs to the end: its pending panel cannot be handed over
-    if (phases_on && ns <= tf_unblocked_below() && ns <= 2048 && phase < 2) {
+    // a single matrix too large for shared memory: once the trailing block fits (order t_smem on all SMs) hand it to the
+    // shared-memory kernel - its sweeps cost half of the L2 ones and its O(n) part handles fewer rows per thread
+    if (handover_on && batch == 1 && phase == 0 && ns > t_smem + 128) jstop = (ns - t_smem) & ~1;
+    else if (phases_on && ns <= tf_unblocked_below() && ns <= 2048 && phase < 2) {
       if (t_cluster > t_solo && ns > t_cluster + 64 && batch <= 8) jstop = ns - t_cluster;
       else if (t_solo > 0 && ns > t_solo + 32) jstop = ns - t_solo;
       jstop &= ~1;
     }
-    const bool prefer_cluster = phases_on && phase > 0 && batch <= 8;
+    const bool prefer_cluster = phases_on && phase > 0 && batch <= 8 && ns <= t_cluster + 64;
     // counters: phase 0 uses [0, 2 cap) (y exchange + the blocked kernel's partial dots), phases 1, 2 one array each
     unsigned* counters = phase == 0 ? ws.bar : ws.bar + (size_t)(phase + 1) * ws.cap;
     const int rc = tf_phase(ns, n, A + (size_t)off * lda + off, lda, sA, ws, ws.d + off, ws.e + off, ws.tau + off, counters,
