@@ -348,7 +348,8 @@ def run_ours(args, w):
                         "share_of_scf_path": ph["panel_kernel"] / max(1e-9, steps[-1]["scf_ms"])}
             if n > 1664 + 128 and P_local * nblk == 1:
                 roofline["launch_note"] = ("one 'launch' = one tridiagonalisation = two kernels: the L2/HBM kernel down "
-                                           "to trailing order 1664, then the shared-memory kernel (hand-over)")
+                                           "to trailing order 1664, then the shared-memory kernel (hand-over); "
+                                           "traffic is the ncu figure of the first kernel only")
         flops_it = 7.0 * n ** 3 + 10.0 * n * n * na
         fp64_tf = flops_it * (iters_all / args.steps / world) * nblk / (dev_s / args.steps) / 1e12 if dev_s > 0 else 0.0
         line = {

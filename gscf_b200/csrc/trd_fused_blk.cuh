@@ -101,9 +101,10 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
   };
 
 #ifdef GSCF_TF_DEBUG_TIMING
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // [0..8) deferred regime, [8..16) unblocked regime
   long long tmark = clock64();
-#define TFB_TICK(k) do { const long long _t = clock64(); tacc[k] += _t - tmark; tmark = _t; } while (0)
+  int treg = 0, tcols[2] = {0, 0};
+#define TFB_TICK(k) do { const long long _t = clock64(); tacc[treg + (k)] += _t - tmark; tmark = _t; } while (0)
 #else
 #define TFB_TICK(k) do { } while (0)
 #endif
@@ -113,6 +114,10 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
     const int first = j + 1;
     double yv[KMAX], rv[KMAX];
     TFB_TICK(7);
+#ifdef GSCF_TF_DEBUG_TIMING
+    treg = (n - j > a_unblocked_below) ? 0 : 8;
+    ++tcols[treg >> 3];
+#endif
     if (j < 0) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
@@ -426,8 +431,13 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
   }
 #ifdef GSCF_TF_DEBUG_TIMING
   if ((tid == 0 || tid == T - 1) && (g == 0 || g == G - 1) && blockIdx.y == 0)
-    printf("cta %d tid %d cycles/col: pubA %lld boundary %lld sweep %lld waitA %lld yfin %lld exchB %lld post %lld loop %lld\n", g, tid,
-           tacc[0] / n, tacc[1] / n, tacc[2] / n, tacc[3] / n, tacc[4] / n, tacc[5] / n, tacc[6] / n, tacc[7] / n);
+    for (int rg = 0; rg < 2; ++rg) {
+      const int nc = max(1, tcols[rg]);
+      const long long* t = tacc + 8 * rg;
+      printf("cta %d tid %d %s (%d cols) cycles/col: pubA %lld boundary %lld sweep %lld waitA %lld yfin %lld exchB %lld post %lld loop %lld\n",
+             g, tid, rg ? "unblocked" : "deferred", tcols[rg], t[0] / nc, t[1] / nc, t[2] / nc, t[3] / nc, t[4] / nc, t[5] / nc,
+             t[6] / nc, t[7] / nc);
+    }
 #endif
   if (g == 0 && tid == 0 && *reinterpret_cast<volatile unsigned*>(a.abort_flag) != 0u)
     (a.d + q * a.dstride)[0] = __longlong_as_double(0x7ff8000000000000LL);

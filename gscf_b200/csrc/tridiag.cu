@@ -624,7 +624,9 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   if (rega_ok < 0) { const char* re = getenv("GSCF_B200_TF_REGA"); rega_ok = (re && re[0] == '0') ? 0 : 1; }
   const bool rega = rega_ok && smem_a && !solo && !cluster && ceil_div(n, G) <= TF_RS && round_up(n, 2) <= 2 * 256 * TF_RP;
   const size_t smem = tf_smem_bytes(n, G, smem_a && !rega);
-  const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : (n <= 4096 ? 512 : 1024);
+  static int t_big = -1;
+  if (t_big < 0) { const char* tb = getenv("GSCF_B200_TF_TBIG"); t_big = tb ? atoi(tb) : 0; }
+  const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : ((n <= 4096 && t_big != 1024) ? 512 : 1024);
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
