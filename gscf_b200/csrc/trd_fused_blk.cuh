@@ -250,25 +250,33 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
         TFB_TICK(1);
       } else {
         // ================= all other columns: read only ===========================================================
+        // two row pairs per thread and pass: 16 independent 16-byte loads in flight per thread (the sweep is bound by
+        // memory latency, not bandwidth: ncu long_scoreboard, profiles/r01_ncu_full_trd_fused.json "4096")
         for (int sg = se; sg < S; sg += TF_CG) {
           double acc[TF_CG];
 #pragma unroll
           for (int u = 0; u < TF_CG; ++u) acc[u] = 0.0;
-          for (int p = tid; p < npairs; p += T) {
-            const int r = r_lo + 2 * p;
-            const double2 vn = *reinterpret_cast<const double2*>(svc + r);
-            double2 x[TF_CG];
+          const double* cb = A + (size_t)(g + sg * G) * lda + r_lo;
+          const size_t cs = (size_t)G * lda;
+          const int umax = S - 1 - sg;  // beyond S: re-read the last column, result discarded
+          for (int p = tid; p < npairs; p += 2 * T) {
+            const int p2 = p + T;
+            const bool h2 = p2 < npairs;
+            const int q2 = h2 ? p2 : p;
+            double2 x0[TF_CG], x1[TF_CG];
+#pragma unroll
+            for (int u = 0; u < TF_CG; ++u) x0[u] = *reinterpret_cast<const double2*>(cb + min(u, umax) * cs + 2 * p);
+#pragma unroll
+            for (int u = 0; u < TF_CG; ++u) x1[u] = *reinterpret_cast<const double2*>(cb + min(u, umax) * cs + 2 * q2);
+            double2 v0 = *reinterpret_cast<const double2*>(svc + r_lo + 2 * p);
+            double2 v1 = *reinterpret_cast<const double2*>(svc + r_lo + 2 * q2);
+            if (r_lo + 2 * p + 1 >= n) v0.y = 0.0;   // odd tail: the pad row is not part of the matrix
+            if (r_lo + 2 * q2 + 1 >= n) v1.y = 0.0;
+            if (!h2) { v1.x = 0.0; v1.y = 0.0; }
 #pragma unroll
             for (int u = 0; u < TF_CG; ++u) {
-              const int slot = sg + u;
-              x[u] = make_double2(0.0, 0.0);
-              if (slot < S) x[u] = *reinterpret_cast<const double2*>(A + (size_t)(g + slot * G) * lda + r);
-            }
-            const bool odd_tail = (r + 1 >= n);
-#pragma unroll
-            for (int u = 0; u < TF_CG; ++u) {
-              const double xy = odd_tail ? 0.0 : x[u].y;
-              acc[u] = fma(x[u].x, vn.x, fma(xy, vn.y, acc[u]));
+              acc[u] = fma(x0[u].x, v0.x, fma(x0[u].y, v0.y, acc[u]));
+              acc[u] = fma(x1[u].x, v1.x, fma(x1[u].y, v1.y, acc[u]));
             }
           }
 #pragma unroll
