@@ -284,8 +284,10 @@ def test_syev_tridiag_dc_fock_like(env):
     (130, 5, {}),                                                                   # one CTA per matrix (SOLO, shared memory)
     (101, 6, {}),                                                                   # one CTA per matrix, registers
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
-    (1024, 2, {"GSCF_B200_TF_FUSED": "0"}),                                         # previous panel kernels still work
+    (1024, 2, {"GSCF_B200_TRD_FUSED": "0"}),                                        # previous panel kernels still work
     (2048, 1, {}),                                                                  # L2 kernel, hand-over to shared memory
+    (1801, 1, {}),                                                                  # shortest L2 phase (136 columns), odd order
+    (2601, 1, {}),                                                                  # deferred updates, unblocked, hand-over
     (700, 1, {"GSCF_B200_TF_HANDOVER": "256"}),                                     # hand-over out of the register kernel
     (700, 1, {"GSCF_B200_TF_GLOBAL": "1", "GSCF_B200_TF_UNBLOCKED_BELOW": "300",
               "GSCF_B200_TF_HANDOVER": "200"}),                                     # hand-over out of the blocked kernel
