@@ -604,6 +604,7 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
   A(&e->fail, P);
   A(&e->eiginfo, PM);
   A(&e->act_p, P);
+  A(&e->keep_p, P);
   A(&e->act_m, PM);
   A(&e->act_mb[0], P);
   A(&e->act_mb[1], P);
@@ -647,7 +648,7 @@ void gscf_b200_engine_destroy(gscf_b200_engine* e) {
   cudaFree(e->Cbuf); cudaFree(e->orben); cudaFree(e->D); cudaFree(e->Aeig); cudaFree(e->Zeig);
   cudaFree(e->Tmp); cudaFree(e->errwork); cudaFree(e->gram); cudaFree(e->coeff); cudaFree(e->dots);
   cudaFree(e->energies); cudaFree(e->scal); cudaFree(e->fail); cudaFree(e->eiginfo);
-  cudaFree(e->eigwork); cudaFree(e->mdwork); cudaFree(e->act_p); cudaFree(e->act_m);
+  cudaFree(e->eigwork); cudaFree(e->mdwork); cudaFree(e->act_p); cudaFree(e->keep_p); cudaFree(e->act_m);
   cudaFree(e->act_mb[0]); cudaFree(e->act_mb[1]);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -954,7 +955,12 @@ int gscf_b200_solve_diis(gscf_b200_engine* e, const gscf_b200_params* prm) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// TruncatedOptDampScf::solve_state (TruncatedOptDampScf.hh:239-289), single problem
+// TruncatedOptDampScf::solve_state (TruncatedOptDampScf.hh:239-289), P problems in lock-step
+//
+// Per problem the reference keeps prev_problem_matrix_ptr (:61), its energies and damping_coeff (:70).  Here the
+// current matrix of every problem lives in one ring slot (CUR) and the kept previous one in another (PREV): when a
+// problem keeps its matrix (:273-275) the matrix is copied CUR -> PREV (one n x n copy per keeper and iteration,
+// nothing against the eigensolve), so that all kernels still see one slot per role for the whole ensemble.
 // ------------------------------------------------------------------------------------------------
 int gscf_b200_solve_toda(gscf_b200_engine* e, const gscf_b200_params* prm) {
   GSCF_TRY(check_ready(e, prm));
@@ -963,121 +969,143 @@ int gscf_b200_solve_toda(gscf_b200_engine* e, const gscf_b200_params* prm) {
     set_last_error("toda_n_prev_steps must be 2");
     return GSCF_B200_ERR_NOT_IMPLEMENTED;
   }
-  if (e->P != 1) {
-    set_last_error("solve_toda drives one problem per engine (ensembles: plain / DIIS)");
-    return GSCF_B200_ERR_NOT_IMPLEMENTED;
-  }
   begin_solve(e);
   IterScalars sc;
   SlotList self{};
   self.n = 1; self.slot[0] = 0;
-  const int n = e->n, ld = e->ld;
-  int prev_slot = -1;                 // prev_problem_matrix_ptr (:61)
-  double e1_prev = 0, e2_prev = 0;    // energies of the matrix in prev_slot
-  double damp = 1.0;                  // damping_coeff (:70, :76)
-  std::vector<double> orb((size_t)e->nblk * n);
-  std::vector<int> act{0};
+  const int n = e->n, ld = e->ld, P = e->P;
+  const int CUR = e->cur_slot;
+  const int PREV = CUR == 0 ? 1 : 0;
+  std::vector<char> prev_valid(P, 0);                 // prev_problem_matrix_ptr != nullptr
+  std::vector<double> e1_prev(P, 0.0), e2_prev(P, 0.0);  // energies of the matrix in PREV
+  std::vector<double> damp(P, 1.0), lam(P, 1.0);      // damping_coeff (:70, :76)
+  std::vector<double> orb, tr4((size_t)P * 4), cf((size_t)P * kMaxHistory, 0.0);
+  std::vector<int> keep;
+  // PREV must hold finite numbers for the problems without a previous matrix (their coefficient is an exact 0)
+  for (int p = 0; p < P; ++p)
+    GSCF_CUDA_TRY(cudaMemsetAsync(e->Fslot(PREV) + p * e->fring_pstride(), 0, (size_t)e->pstride * sizeof(double), e->stream));
   {
     Span total(e, PH_TOTAL, true);
-    GSCF_TRY(upload_active(e));
+    bool first = true;
     while (true) {
-      update_active(e, prm);
-      if (!e->active[0]) break;
-      e->n_iter[0]++;
-      const int it = e->n_iter[0];
+      const bool changed = update_active(e, prm);
+      const int nact = n_active(e);
+      if (nact == 0) break;
+      if (changed || first) GSCF_TRY(upload_active(e));
+      first = false;
+      std::vector<int> act;
+      for (int p = 0; p < P; ++p) if (e->active[p]) { act.push_back(p); e->n_iter[p]++; }
+      const int it = e->n_iter[act[0]];
       GSCF_TRY(call_hook(e, GSCF_B200_EV_BEFORE_ITERATION, it));
       // ---- update_damping_coefficients (:349-368) -------------------------------------------------
       {
         Span sp(e, PH_COEFF);
-        if (prev_slot < 0) {
-          damp = 1.0;
-        } else {
+        bool need_short = false, need_gemm = false;
+        for (int p : act)
+          if (prev_valid[p]) (damp[p] == 1 ? need_short : need_gemm) = true;
+        if (need_short) {  // trace_fprev_dcur shortcut (:309-319): sums of occupied orbital energies
+          orb.resize((size_t)P * e->nblk * n);
+          GSCF_CUDA_TRY(cudaMemcpyAsync(orb.data(), e->orben_cur(), orb.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        }
+        if (need_gemm) {  // :325-345: tr(C_o^T F_prev C_o) per block, never forming the n x n product
+          for (int b = 0; b < e->nblk; ++b) {
+            const int o = e->occ[b];
+            GemmParams g = gemm_params(n, o, n, 1.0, e->Fslot(PREV) + b * e->mstride, ld, e->Ccur() + b * e->mstride, ld,
+                                       0.0, e->Tmp + b * e->mstride, ld);
+            g.sA = e->fring_pstride(); g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p;
+            GSCF_TRY(launch_gemm(false, false, g, nact, n, o, e->stream));
+            GSCF_TRY(multidot(e->Ccur() + b * e->mstride, e->pstride, e->Tmp + b * e->mstride, 0, e->pstride, self, n, o,
+                              ld, nact, e->act_p, e->scal + b, 4, e->mdwork, e->stream));
+          }
+          GSCF_CUDA_TRY(cudaMemcpyAsync(tr4.data(), e->scal, tr4.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        }
+        if (need_short || need_gemm) GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+        for (int p : act) {
+          if (!prev_valid[p]) { damp[p] = 1.0; continue; }
           double tr;
-          if (damp == 1) {  // trace_fprev_dcur shortcut (:309-319)
-            GSCF_CUDA_TRY(cudaMemcpyAsync(orb.data(), e->orben_cur(), orb.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-            GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+          if (damp[p] == 1) {
+            const double* w = orb.data() + (size_t)p * e->nblk * n;
             double sum_a = 0.0;
-            for (int i = 0; i < e->occ[0]; ++i) sum_a += orb[i];
+            for (int i = 0; i < e->occ[0]; ++i) sum_a += w[i];
             if (e->nblk == 1) {
               tr = 2. * sum_a;
             } else {
-              double s = sum_a;
-              for (int i = 0; i < e->occ[1]; ++i) s += orb[(size_t)n + i];
-              tr = s;
+              double s2 = sum_a;
+              for (int i = 0; i < e->occ[1]; ++i) s2 += w[(size_t)n + i];
+              tr = s2;
             }
-          } else {  // :325-345: tr(C_o^T F_prev C_o) per block, never forming the n x n product
-            e->n_mtx_applies[0] += 1;
-            double trb[2] = {0, 0};
-            for (int b = 0; b < e->nblk; ++b) {
-              const int o = e->occ[b];
-              GSCF_TRY(gemm(false, false, n, o, n, 1.0, e->Fslot(prev_slot) + b * e->mstride, ld,
-                            e->Ccur() + b * e->mstride, ld, 0.0, e->Tmp, ld, e->stream));
-              SlotList one{};
-              one.n = 1; one.slot[0] = 0;
-              GSCF_TRY(multidot(e->Ccur() + b * e->mstride, 0, e->Tmp, 0, 0, one, n, o, ld, 1, nullptr,
-                                e->scal + b, 1, e->mdwork, e->stream));
-            }
-            GSCF_CUDA_TRY(cudaMemcpyAsync(trb, e->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-            GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
-            tr = e->nblk == 1 ? 2. * trb[0] : trb[0] + trb[1];
+          } else {
+            e->n_mtx_applies[p] += 1;
+            tr = e->nblk == 1 ? 2. * tr4[(size_t)p * 4] : tr4[(size_t)p * 4] + tr4[(size_t)p * 4 + 1];
           }
-          const double oda_s = tr - e1_prev - 2. * e2_prev;                 // :360-361
-          const double oda_c = e->e1[0] - tr + e->e2[0] + e2_prev;         // :362-364
-          damp = compute_damping_coeff(oda_s, oda_c, prm->toda_min_fock_prefactor);
-          if (damp == 1) prev_slot = -1;                                   // :367
+          const double oda_s = tr - e1_prev[p] - 2. * e2_prev[p];              // :360-361
+          const double oda_c = e->e1[p] - tr + e->e2[p] + e2_prev[p];          // :362-364
+          damp[p] = compute_damping_coeff(oda_s, oda_c, prm->toda_min_fock_prefactor);
+          if (damp[p] == 1) prev_valid[p] = 0;                                 // :367
         }
       }
-      e->damp[0] = damp;
+      for (int p : act) e->damp[p] = damp[p];
       // ---- update_oda_diagmat (:396-409) -------------------------------------------------------------
       const double* Fd;
       long long fd_pstride;
       {
         Span sp(e, PH_DIAGMAT);
-        if (prev_slot < 0) {
+        bool any_prev = false;
+        for (int p : act) any_prev = any_prev || prev_valid[p];
+        if (!any_prev) {
           e->diagmat_kind = 0;
-          Fd = e->Fslot(e->cur_slot); fd_pstride = e->fring_pstride();
+          Fd = e->Fslot(CUR); fd_pstride = e->fring_pstride();
           e->n_coeff = 0;
         } else {
           e->diagmat_kind = 2;
           SlotList two{};
-          two.n = 2; two.slot[0] = prev_slot; two.slot[1] = e->cur_slot;
-          const double cf[2] = {1. - damp, damp};
-          GSCF_CUDA_TRY(cudaMemcpyAsync(e->coeff, cf, 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+          two.n = 2; two.slot[0] = PREV; two.slot[1] = CUR;
+          for (int p : act) {  // no previous matrix: 0 * PREV + 1 * CUR is CUR exactly
+            cf[(size_t)p * kMaxHistory] = prev_valid[p] ? 1. - damp[p] : 0.0;
+            cf[(size_t)p * kMaxHistory + 1] = prev_valid[p] ? damp[p] : 1.0;
+          }
+          GSCF_CUDA_TRY(cudaMemcpyAsync(e->coeff, cf.data(), cf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
           GSCF_TRY(axpby_n(e->Fdiag, e->pstride, e->Fring, e->pstride, e->fring_pstride(), two, e->coeff,
-                           kMaxHistory, n, n * e->nblk, ld, 1, nullptr, e->stream));
+                           kMaxHistory, n, n * e->nblk, ld, nact, e->act_p, e->stream));
           Fd = e->Fdiag; fd_pstride = e->pstride;
           e->n_coeff = 2;
         }
       }
       GSCF_TRY(call_hook(e, GSCF_B200_EV_NEW_DIAGMAT, it));
-      GSCF_TRY(step_eigensolve(e, Fd, fd_pstride, 1));  // :253
+      GSCF_TRY(step_eigensolve(e, Fd, fd_pstride, nact));  // :253
       GSCF_TRY(call_hook(e, GSCF_B200_EV_UPDATE_EIGENPAIRS, it));
-      const double lam = damp;
       // ---- keep / flip (:273-277) ---------------------------------------------------------------------
-      if (damp > 0.5) {
-        prev_slot = e->cur_slot;
-        e1_prev = e->e1[0]; e2_prev = e->e2[0];
-      } else {
-        damp = 1 - damp;
+      keep.clear();
+      for (int p : act) {
+        lam[p] = damp[p];
+        if (damp[p] > 0.5) {
+          keep.push_back(p);
+          prev_valid[p] = 1;
+          e1_prev[p] = e->e1[p]; e2_prev[p] = e->e2[p];
+        } else {
+          damp[p] = 1 - damp[p];
+        }
+        e->damp[p] = damp[p];
       }
-      e->damp[0] = damp;
-      // ---- update_problem_matrix (:282): write into a slot that neither prev nor ... aliases -------------
-      int slot = -1;
-      const int cand[3] = {0, 1, e->M};
-      for (int c : cand)
-        if (c != prev_slot) { slot = c; break; }
-      GSCF_TRY(step_density(e, 1));
-      GSCF_TRY(step_fock(e, slot, 1, act));
+      if (!keep.empty()) {
+        GSCF_CUDA_TRY(cudaMemcpyAsync(e->keep_p, keep.data(), keep.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        GSCF_TRY(scale_copy(e->Fslot(PREV), ld, e->fring_pstride(), e->Fslot(CUR), ld, e->fring_pstride(), 1.0, n,
+                            n * e->nblk, (int)keep.size(), e->keep_p, e->stream));
+        GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));  // `keep` is reused next iteration
+      }
+      // ---- update_problem_matrix (:282): in place, the kept copy is in PREV --------------------------------
+      GSCF_TRY(step_density(e, nact));
+      GSCF_TRY(step_fock(e, CUR, nact, act));
       GSCF_TRY(call_hook(e, GSCF_B200_EV_UPDATE_PROBLEM_MATRIX, it));
       {
         Span sp(e, PH_ERROR);
-        GSCF_TRY(step_error(e, slot, e->Eslot(0), e->ering_pstride(), 1));  // :285
-        GSCF_TRY(step_multidot(e, e->Eslot(0), e->ering_pstride(), self, 1));
+        GSCF_TRY(step_error(e, CUR, e->Eslot(0), e->ering_pstride(), nact));  // :285
+        GSCF_TRY(step_multidot(e, e->Eslot(0), e->ering_pstride(), self, nact));
       }
       e->last_error_slot = 0;
       GSCF_TRY(fetch_scalars(e, sc));
       absorb_scalars(e, sc, 0, false);
-      record_trace(e, 0, &lam, 1);
+      for (int p : act) record_trace(e, p, &lam[p], 1);
       GSCF_TRY(call_hook(e, GSCF_B200_EV_AFTER_ITERATION, it));
     }
   }

@@ -46,6 +46,7 @@ struct gscf_b200_engine {
   size_t eigwork_bytes = 0;
   double* mdwork = nullptr;
   int* act_p = nullptr;     // active problems
+  int* keep_p = nullptr;    // TODA: problems that keep their matrix this iteration
   int* act_m = nullptr;     // active matrices (p*nblk+b)
   int* act_mb[2] = {nullptr, nullptr};
   // pinned host staging

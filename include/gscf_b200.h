@@ -235,7 +235,9 @@ int gscf_b200_set_guess_from_matrix(gscf_b200_engine* e, const double* G, int ld
 
 /* Whole-loop, device-resident drivers (PlainScf.hh:121-147, PulayDiisScf.hh:283-324,
  * TruncatedOptDampScf.hh:239-289).  Return GSCF_B200_OK when every problem converged;
- * GSCF_B200_ERR_MAX_ITER etc. otherwise (per-problem flags via the getters). */
+ * GSCF_B200_ERR_MAX_ITER etc. otherwise (per-problem flags via the getters).  All three run the
+ * engine's P problems in lock-step; a problem leaves the active set when it converges or fails
+ * (TODA: damping coefficient, keep/flip decision and previous matrix are per problem). */
 int gscf_b200_solve_plain(gscf_b200_engine* e, const gscf_b200_params* p);
 int gscf_b200_solve_diis(gscf_b200_engine* e, const gscf_b200_params* p);
 int gscf_b200_solve_toda(gscf_b200_engine* e, const gscf_b200_params* p);

@@ -251,6 +251,46 @@ def test_ensemble_lockstep(G):
     assert len(set(its.tolist())) > 1  # members really stop at different iterations
 
 
+@pytest.mark.parametrize("n,na,nb,aux,P", [(64, 8, 8, 8, 10), (48, 6, 5, 6, 6)])
+def test_ensemble_toda_lockstep(G, n, na, nb, aux, P):
+    """TruncatedOptDampScf on an ensemble in one engine: every member (its own damping coefficients, keep/flip
+    decisions and stopping iteration) equals its single-problem oracle run (TruncatedOptDampScf.hh:239-409)."""
+    seeds = list(range(40, 40 + P))
+    fock = G.DeviceDFFock(n, na, nb, n_aux=aux, seeds=seeds)
+    eng, st = G.solve_device_problem(fock, "toda", {"max_error_norm": 1e-5, "max_iter": 80})
+    try:
+        its = eng.n_iter()
+        e1, e2 = eng.energies()
+        conv = eng.converged()
+        w = eng.orben()
+        damp = eng.damping_coeff()
+        traces = [eng.trace(p) for p in range(P)]
+    finally:
+        eng.close()
+        fock.close()
+    from oracle import ScfFailed
+    n_checked, damped = 0, 0
+    for i, s in enumerate(seeds):
+        try:
+            ref, _ = _oracle_synthetic(n, na, aux, "toda", seed=s, n_beta=None if na == nb else nb,
+                                       max_error_norm=1e-5, max_iter=80)
+        except ScfFailed:
+            assert conv[i] == 0
+            continue
+        assert conv[i] == 1
+        assert its[i] == ref.n_iter, (i, its[i], ref.n_iter)
+        assert abs(e1[i] + e2[i] - ref.energy_total) < TOL_E
+        assert np.abs(w[i] - ref.orben).max() < 1e-6
+        lam = [float(c[0]) for c in traces[i][2]]
+        np.testing.assert_allclose(lam[:6], ref.trace_coeff[:6], rtol=1e-6, atol=1e-8)
+        damped += int(min(lam) < 0.9)
+        n_checked += 1
+    assert n_checked >= P // 2
+    assert damped >= 1                      # the damped branch ran for some member
+    assert len(set(its.tolist())) > 1       # members stop at different iterations
+    assert damp.shape[0] == P
+
+
 @pytest.mark.parametrize("n,o,aux,m", [(160, 20, 8, 4), (256, 32, 16, 8)])
 def test_synthetic_parity_large_path(G, n, o, aux, m):
     """DIIS through the tridiagonalisation + divide&conquer eigensolver (n > 128)."""
