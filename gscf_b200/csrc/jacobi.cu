@@ -34,7 +34,7 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
   double* G = sm;                      // ne * ldg
   double* lam = G + (size_t)ne * ldg;  // ne
   __shared__ double s_red[33];
-  __shared__ double s_sigma;
+  __shared__ double s_sigma, s_scale;
 
   const long long prob = batch_map ? batch_map[blockIdx.x] : blockIdx.x;
   const double* A = Ain + prob * strideA;
@@ -61,10 +61,18 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
   if (tid == 0) {
     double m = 0.0;
     for (int i = 0; i < nwarp; ++i) m = fmax(m, s_red[i]);
+    // dsyev's scaling: the squared column norms of a matrix far from unit norm leave the double range
+    const bool ext = m > 0.0 && isfinite(m) && (m < 1e-100 || m > 1e100);
+    s_scale = ext ? m : 1.0;
+    if (ext) m = 1.0;
     s_sigma = (m > 0.0 && isfinite(m)) ? 2.0 * m : 1.0;
   }
   __syncthreads();
-  const double sigma = s_sigma;
+  const double sigma = s_sigma, ascale = s_scale;
+  if (ascale != 1.0) {
+    for (int idx = tid; idx < ne * ldg; idx += nthr) G[idx] /= ascale;
+    __syncthreads();
+  }
   for (int c = tid; c < n; c += nthr) G[(size_t)c * ldg + c] += sigma;
   __syncthreads();
 
@@ -185,7 +193,7 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
     const double nrm = sqrt(s);
     const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
     for (int r = lane; r < n; r += 32) g[r] *= inv;
-    if (lane == 0) lam[c] = nrm - sigma;
+    if (lane == 0) lam[c] = (nrm - sigma) * ascale;
   }
   __syncthreads();
   // garbage in (NaN / Inf) must be reported, not sorted into a plausible-looking spectrum

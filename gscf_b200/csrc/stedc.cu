@@ -45,6 +45,42 @@ __device__ inline NodeGeom node_geom(int t, int h, int n, int L) {
   return g;
 }
 
+// ---- scaling ------------------------------------------------------------------------------------------
+// dstedc scales T to unit max-norm first: the deflation tolerance of a merge, 8 eps max(|d|, |z|) with |z| <= 1, is an
+// absolute quantity (unscaled, a matrix of norm 1e-3 would lose three digits and one of norm 1e-150 everything).
+__global__ void __launch_bounds__(256)
+dc_scale_kernel(double* __restrict__ d, double* __restrict__ e, long long dstride, StedcWs ws,
+                const int* __restrict__ map) {
+  __shared__ double red[8];
+  const long long q = map ? map[blockIdx.x] : blockIdx.x;
+  const int n = ws.n;
+  double* dq = d + q * dstride;
+  double* eq = e + q * dstride;
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    m = fmax(m, fabs(dq[i]));
+    if (i < n - 1) m = fmax(m, fabs(eq[i]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.0;
+  for (int w = 0; w < 8; ++w) m = fmax(m, red[w]);
+  const double s = (m > 0.0 && isfinite(m)) ? m : 1.0;
+  // entries below 1e-140 of the norm become exact zeros: the tridiagonalisation of a (numerically) low-rank matrix
+  // leaves a cascade of ever smaller noise (1e-16, 1e-32, ... 1e-160) whose squares are subnormal, and the rotations
+  // of the QL leaves computed from them are not orthogonal.  A zero e splits the problem instead.
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double dv = dq[i] / s;
+    dq[i] = fabs(dv) < 1e-140 ? 0.0 : dv;   // NaN compares false: kept, flagged at the end
+    if (i < n - 1) {
+      const double ev = eq[i] / s;
+      eq[i] = fabs(ev) < 1e-140 ? 0.0 : ev;
+    }
+  }
+  if (threadIdx.x == 0) ws.scale[q] = s * (ws.outer ? ws.outer[q] : 1.0);
+}
+
 // ---- leaves ------------------------------------------------------------------------------------------
 __global__ void dc_split_kernel(const double* __restrict__ d, const double* __restrict__ e, long long dstride,
                                 StedcWs ws, const int* __restrict__ map) {
@@ -561,7 +597,7 @@ __global__ void dc_permute_kernel(StedcWs ws, int lev, const double* __restrict_
   double* y = Zout + q * sout + (size_t)r * ldout;
   for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
   if (threadIdx.x == 0) {
-    const double l = (ws.lam[lev] + q * n)[j];
+    const double l = (ws.lam[lev] + q * n)[j] * ws.scale[q];
     (w + q * stride_w)[r] = l;
     if (!isfinite(l) && info) info[q] = 1;
   }
@@ -593,6 +629,7 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
   ws.dlamda = (double*)take(cn * 8); ws.w = (double*)take(cn * 8); ws.zhat = (double*)take(cn * 8);
   ws.rot_c = (double*)take(cn * 8); ws.rot_s = (double*)take(cn * 8);
   ws.rho = (double*)take((size_t)cap * ws.nleaf * 8);
+  ws.scale = (double*)take((size_t)cap * 8);
   ws.idx = (int*)take(cn * 4); ws.ctype = (int*)take(cn * 4); ws.ndcol = (int*)take(cn * 4);
   ws.dcol = (int*)take(cn * 4); ws.gpos = (int*)take(cn * 4); ws.rot_a = (int*)take(cn * 4);
   ws.rot_b = (int*)take(cn * 4); ws.rank = (int*)take(cn * 4);
@@ -611,7 +648,7 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
   return off;
 }
 
-int stedc_batched(int n, const double* d, const double* e, long long dstride, double* w, long long stride_w,
+int stedc_batched(int n, double* d, double* e, long long dstride, double* w, long long stride_w,
                   double* Z, int ldz, long long strideZ, const StedcWs& ws, int batch, const int* map,
                   int* info_dev, cudaStream_t st) {
   if (batch <= 0) return GSCF_B200_OK;
@@ -624,6 +661,8 @@ int stedc_batched(int n, const double* d, const double* e, long long dstride, do
   bufp[0] = Z; bufld[0] = ldz; bufs[0] = strideZ;
   bufp[1] = ws.Zb; bufld[1] = ws.ld; bufs[1] = (long long)ws.ld * n;
   int cur = first;
+  dc_scale_kernel<<<batch, 256, 0, st>>>(d, e, dstride, ws, map);
+  count_launch(1);
   // ---- leaves -----------------------------------------------------------------------------------------
   dc_split_kernel<<<dim3(std::max(1, ceil_div(n, 256)), batch), 256, 0, st>>>(d, e, dstride, ws, map);
   count_launch(1);

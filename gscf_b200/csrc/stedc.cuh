@@ -18,6 +18,8 @@ struct StedcWs {
   double* rot_c = nullptr;              // [cap][n]
   double* rot_s = nullptr;              // [cap][n]
   double* rho = nullptr;                // [cap][nleaf]
+  double* scale = nullptr;              // [cap] factor of the eigenvalues: max-norm of T (the D&C runs on T / norm) x outer
+  const double* outer = nullptr;        // [cap] optional: what the caller divided the dense matrix by (1 if nothing)
   int* idx = nullptr;                   // [cap][n]
   int* ctype = nullptr;                 // [cap][n]
   int* ndcol = nullptr;                 // [cap][n]
@@ -42,9 +44,9 @@ struct StedcWs {
 // base == nullptr only the size is computed.
 size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws);
 
-// T = tridiag(d, e) (n entries each with stride dstride per matrix; e[0..n-2]) ->
+// T = tridiag(d, e) (n entries each with stride dstride per matrix; e[0..n-2]; scaled in place to unit max-norm) ->
 // w ascending (stride_w per matrix) and eigenvectors Z (n x n, ldz, strideZ).
-int stedc_batched(int n, const double* d, const double* e, long long dstride, double* w,
+int stedc_batched(int n, double* d, double* e, long long dstride, double* w,
                   long long stride_w, double* Z, int ldz, long long strideZ, const StedcWs& ws,
                   int batch, const int* batch_map, int* info_dev, cudaStream_t st);
 

@@ -39,6 +39,8 @@ struct TrdWs {
   double* scal;         // [cap][8]   0: a[i+1]  1: raw w[i+1]
   unsigned* bar;        // [cap] group barrier counters of the persistent panel kernel
   double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
+  unsigned long long* amax;  // [cap] max |a_ij| (bit pattern)
+  double* ascale;       // [cap] 1, or the norm an extreme matrix was divided by
   double* SK;           // split-k partials: min(cap,16) * 16 * NBQ * n
   double* X;            // [cap][4 np] exchange slots of the fused tridiagonalisation (trd_fused.cuh)
   double* VPW;          // [cap][2][32][np] pending reflector panels of the blocked fused kernel
@@ -59,8 +61,10 @@ inline int ws_cap_hint(const TrdWs& ws) { return ws.cap; }
 
 __device__ __forceinline__ void householder_scalars(double alpha, double xnorm2, double& beta, double& tau,
                                                      double& scale) {
-  // LAPACK dlarfg without the safe-minimum rescaling loop
-  if (xnorm2 == 0.0) {
+  // LAPACK dlarfg.  Instead of its safe-minimum rescaling loop: a sum of squares below safmin / eps carries no
+  // relative accuracy (subnormal squares), and a reflector built from it is not orthogonal - such a column (entries
+  // below 1e-146 in a matrix that tridiag_dc_syev_batched has scaled to a sane norm) is treated as exactly zero.
+  if (xnorm2 < 1e-292) {
     beta = alpha; tau = 0.0; scale = 0.0;
   } else {
     beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
@@ -276,6 +280,47 @@ trd_finalize_w(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, i
   if (r < n) W[(size_t)li * ws.ld + r] += s_alpha * A[(size_t)i * lda + r];
 }
 
+// ---- scaling of extreme matrices (dsyev: anrm outside [rmin, rmax]) ---------------------------------------------------
+// max |a_ij| per matrix as the bit pattern of a non-negative double (ordered like the integers); NaN sorts above inf
+__global__ void __launch_bounds__(256)
+absmax_kernel(const double* __restrict__ Ab, int lda, long long sA, int n, unsigned long long* __restrict__ amax,
+              const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const double* A = Ab + q * sA;
+  unsigned long long m = 0ull;
+  const long long total = (long long)lda * n;  // the pad rows are part of the buffer (zero or finite garbage is harmless:
+  (void)total;                                  // only rows < n are read)
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)n * n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / n), r = (int)(idx - (long long)c * n);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(A[(size_t)c * lda + r]));
+    m = b > m ? b : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = t > m ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(amax + q, m);
+}
+
+// A <- A / anrm when anrm is outside [1e-100, 1e100]; ascale = the factor the eigenvalues are multiplied with at the end
+__global__ void __launch_bounds__(256)
+scale_extreme_kernel(double* __restrict__ Ab, int lda, long long sA, int n, const unsigned long long* __restrict__ amax,
+                     double* __restrict__ ascale, const int* __restrict__ map) {
+  const long long q = map ? map[blockIdx.y] : blockIdx.y;
+  const double a = __longlong_as_double((long long)amax[q]);
+  const bool ext = a > 0.0 && isfinite(a) && (a < 1e-100 || a > 1e100);
+  if (blockIdx.x == 0 && threadIdx.x == 0) ascale[q] = ext ? a : 1.0;
+  if (!ext) return;
+  double* A = Ab + q * sA;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)n * n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx / n), r = (int)(idx - (long long)c * n);
+    A[(size_t)c * lda + r] /= a;
+  }
+}
+
 // ---- back-transformation helpers ---------------------------------------------------------------------
 // T (pw x pw upper triangular, the dlarft factor) from G = V^T V and tau through T^-1 = diag(1/tau) + striu(G):
 // column c of T solves the triangular system by back substitution,
@@ -368,6 +413,8 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.PQ = cv.take<double>((size_t)cap * 2 * 256 * 64);
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
   ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
+  ws.amax = cv.take<unsigned long long>((size_t)cap);
+  ws.ascale = cv.take<double>((size_t)cap);
   ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
@@ -987,6 +1034,17 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
   StedcWs dws;
   stedc_carve((char*)work, cv.off, n, cap, dws);
   phase_mark(PH_TRIDIAG, true, st);
+  {
+    // dsyev's scaling: a matrix whose norm is far from 1 is divided by it, the eigenvalues are multiplied back at the end
+    // (squares of entries below 1e-154 / above 1e154 leave the double range in the reflector norms)
+    GSCF_CUDA_TRY(cudaMemsetAsync(ws.amax, 0, (size_t)cap * sizeof(unsigned long long), st));
+    const int gx = std::max(1, std::min(ceil_div(n * n, 256 * 16), std::max(1, 148 * 8 / batch)));
+    absmax_kernel<<<dim3(gx, batch), 256, 0, st>>>(A, lda, strideA, n, ws.amax, batch_map);
+    scale_extreme_kernel<<<dim3(gx, batch), 256, 0, st>>>(A, lda, strideA, n, ws.amax, ws.ascale, batch_map);
+    count_launch(2);
+    GSCF_CHECK_LAUNCH();
+    dws.outer = ws.ascale;
+  }
   GSCF_TRY(tridiagonalise(n, A, lda, strideA, ws, batch, batch_map, st));
   phase_mark(PH_TRIDIAG, false, st);
   // fork: the block factors of the back-transformation on a side stream, concurrently with the D&C stage

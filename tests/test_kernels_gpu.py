@@ -275,6 +275,28 @@ def test_syev_tridiag_dc_fock_like(env):
     _syev_check(torch, L, L.EIG_TRIDIAG_DC, [A, X @ p.H @ X], 384)
 
 
+@pytest.mark.parametrize("n", [17, 64, 129, 256, 700])
+def test_syev_special_matrices(env, n):
+    """Zero / identity / rank-one / extreme-norm / glued-Wilkinson / graded matrices in one batch (scripts/eig_stress.py
+    is the long version).  The all-ones matrix is the hard one: its tridiagonal form carries a cascade of noise down to
+    1e-160 whose squares are subnormal (reflector norms, QL rotations); 1e+-150 matrices need dsyev's scaling, and the
+    deflation tolerances of the D&C merges need dstedc's scaling of T to unit norm."""
+    torch, L = env
+    from scripts.eig_stress import kinds, run  # repo root is on sys.path (tests/conftest.py)
+
+    names, mats = zip(*kinds(n, np.random.default_rng(n)))
+    info, W, Z = run(L.EIG_AUTO, n, list(mats))
+    for b, (name, a) in enumerate(zip(names, mats)):
+        wref = np.linalg.eigvalsh(a)
+        scale = max(np.abs(wref).max(), np.finfo(float).tiny)
+        z = Z[b].T
+        tol = 2e-13 * n
+        assert info[b] == 0, name
+        assert np.abs(W[b] - wref).max() / scale < tol, name
+        assert np.abs(z.T @ z - np.eye(n)).max() < tol, name
+        assert np.abs(a @ z - z * W[b]).max() / scale < tol, name
+
+
 @pytest.mark.parametrize("n,batch,envs", [
     (333, 2, {"GSCF_B200_TF_GLOBAL": "1"}),                                        # trailing matrix in global memory
     (600, 1, {"GSCF_B200_TF_GLOBAL": "1", "GSCF_B200_TF_UNBLOCKED_BELOW": "64"}),   # blocked (deferred updates)
