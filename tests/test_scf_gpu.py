@@ -251,6 +251,16 @@ def test_ensemble_lockstep(G):
     assert len(set(its.tolist())) > 1  # members really stop at different iterations
 
 
+def test_randomised_parity_sweep(G):
+    """40 random (n, occupations, solver, DIIS depth, ensemble size, eigensolver) cases against the oracle
+    (scripts/scf_fuzz.py; the reference links rapidcheck for property tests but ships none)."""
+    from scripts.scf_fuzz import main
+
+    bad, checked = main(40, 200)
+    assert bad == 0
+    assert checked >= 40
+
+
 @pytest.mark.parametrize("n,na,nb,aux,P", [(64, 8, 8, 8, 10), (48, 6, 5, 6, 6)])
 def test_ensemble_toda_lockstep(G, n, na, nb, aux, P):
     """TruncatedOptDampScf on an ensemble in one engine: every member (its own damping coefficients, keep/flip
