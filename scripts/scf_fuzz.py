@@ -50,8 +50,12 @@ def main(n_cases=None, first=None):
         if which == "diis":
             params["diis_n_prev_steps"] = m
             kw["n_prev_steps"] = m
+        keig = n
+        if rng.random() < 0.3:  # partial spectrum (ScfBase.hh:87): same iterates, only the lowest k pairs are returned
+            keig = int(rng.integers(max(na, nb), n + 1))
+            params["n_eigenpairs"] = keig
         seeds = [5000 + 10 * case + i for i in range(P)]
-        desc = f"case {case}: n={n} na={na} nb={nb} aux={aux} {which} m={m} P={P} eig={eig} thr={thr:g}"
+        desc = f"case {case}: n={n} na={na} nb={nb} aux={aux} {which} m={m} P={P} eig={eig} thr={thr:g} k={keig}"
         fock = G.DeviceDFFock(n, na, nb, n_aux=aux, seeds=seeds)
         try:
             eng, st = G.solve_device_problem(fock, which, params, eig_method=eig)
@@ -86,10 +90,10 @@ def main(n_cases=None, first=None):
                 continue
             ok = (conv[i] == 1 and its[i] == ref.n_iter and abs(e1[i] + e2[i] - ref.energy_total) < 1e-10)
             tol_w = 1e-6 if which == "toda" else 1e-9
-            ok = ok and np.abs(w[i] - ref.orben).max() < tol_w
+            ok = ok and np.abs(w[i][:, :keig] - ref.orben[:, :keig]).max() < tol_w
             if not ok:
                 print("FAIL", desc, "member", i, "iters", its[i], ref.n_iter, "conv", conv[i], "status", status[i],
-                      "dE", abs(e1[i] + e2[i] - ref.energy_total), "dw", np.abs(w[i] - ref.orben).max(), flush=True)
+                      "dE", abs(e1[i] + e2[i] - ref.energy_total), "dw", np.abs(w[i][:, :keig] - ref.orben[:, :keig]).max(), flush=True)
                 bad += 1
             else:
                 checked += 1
