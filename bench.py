@@ -286,6 +286,8 @@ def run_ours(args, w):
             its = its + its1
             scf_ms, fock_ms = scf_ms + scf1, fock_ms + fock1
         ph = eng.phase_timings()
+        fock_ms += ph["guess_fock"]  # F(C_guess): the plugin's time, like every other Fock build (the reference arm
+        #                              builds F0 outside its timed region too)
         return dict(status=st, iters=its.copy(), e=(e1 + e2).copy(), conv=eng.converged().copy(), wall=wall,
                     scf_ms=scf_ms, fock_ms=fock_ms, overlap_ms=ph["overlap"], ph=ph,
                     d2h=C_host.numel() * 8 + w_host.numel() * 8 + e_host.numel() * 8)

@@ -63,6 +63,7 @@ void collect_timings(Engine* e) {
   e->fock_ms = e->phase_ms[PH_FOCK];
   e->scf_ms = e->phase_ms[PH_TOTAL] - e->fock_ms;
   e->phase_ms[7] = e->overlap_ms;
+  e->phase_ms[14] = e->guess_fock_ms;
 }
 
 thread_local Engine* g_cur_engine = nullptr;
@@ -763,10 +764,22 @@ int gscf_b200_set_guess(gscf_b200_engine* e, const double* C, int ld, int memloc
   std::vector<int> act(e->P);
   for (int p = 0; p < e->P; ++p) act[p] = p;
   GSCF_TRY(step_density(e, e->P));
+  cudaEvent_t fk_a = nullptr, fk_b = nullptr;
+  cudaEventCreate(&fk_a);
+  cudaEventCreate(&fk_b);
+  cudaEventRecord(fk_a, e->stream);
   GSCF_TRY(step_fock(e, e->M, e->P, act));  // ScfStateBase.hh:301-302
+  cudaEventRecord(fk_b, e->stream);
   std::vector<double> en((size_t)e->P * 2);
   GSCF_CUDA_TRY(cudaMemcpyAsync(en.data(), e->energies, en.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, fk_a, fk_b);
+    e->guess_fock_ms = ms;  // the plugin's share of installing the guess (phase 14): not part of the SCF path
+    cudaEventDestroy(fk_a);
+    cudaEventDestroy(fk_b);
+  }
   for (int p = 0; p < e->P; ++p) { e->e1[p] = en[2 * p]; e->e2[p] = en[2 * p + 1]; }
   e->ev_spans.clear();
   e->ev_used = 0;

@@ -78,6 +78,7 @@ struct gscf_b200_engine {
   void* hook_ctx = nullptr;
   // timings
   double scf_ms = 0.0, fock_ms = 0.0, overlap_ms = 0.0;
+  double guess_fock_ms = 0.0;  // Fock-builder time inside the last set_guess
   bool phase_timing = false;
   double phase_ms[16] = {0};
   long long phase_count[16] = {0};

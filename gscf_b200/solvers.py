@@ -414,7 +414,7 @@ class Engine:
         L.check(L.lib.gscf_b200_get_phase_timings(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), 32))
         names = {0: "diagmat", 1: "eig", 2: "density", 3: "error", 4: "coeff", 5: "fock", 6: "total", 7: "overlap",
                  8: "tridiag", 9: "stedc", 10: "backtransform", 11: "panel_kernel", 12: "ortho_gemm",
-                 13: "trailing_gemm"}
+                 13: "trailing_gemm", 14: "guess_fock"}
         res = {v: float(out[k]) for k, v in names.items()}
         res["counts"] = {v: int(out[16 + k]) for k, v in names.items()}
         return res

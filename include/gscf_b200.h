@@ -276,7 +276,9 @@ int gscf_b200_get_trace(gscf_b200_engine* e, int problem, double* energy, double
  * builder) and inside the Fock builder. */
 int gscf_b200_get_timings(gscf_b200_engine* e, double* scf_ms, double* fock_ms);
 /* Per-phase device time of the last solve, ms: [0] extrapolate/diagmat, [1] eigensolve,
- * [2] density, [3] error + overlaps, [4] coefficient solve. */
+ * [2] density, [3] error + overlaps, [4] coefficient solve, [5] Fock builder, [6] whole loop,
+ * [7] orthogonaliser set-up, [8..10] tridiagonalisation / D&C / back-transformation,
+ * [14] Fock builder inside the last gscf_b200_set_guess. */
 int gscf_b200_get_phase_timings(gscf_b200_engine* e, double* ms, int n);
 int gscf_b200_set_phase_timing(gscf_b200_engine* e, int enabled);
 
