@@ -95,9 +95,9 @@ inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
 // vectors, no counter, no global round trip.
 // REGA: the CTA's columns live in REGISTERS (n <= 1024 on >= n/8 CTAs: 8 columns x 4 rows per thread): the sweep was
 // bound by shared-memory bandwidth (17 LDS/STS.128 per row pair), with the matrix in registers it only reads the
-// three vectors.  Thread t owns rows 2 (t + T p), 2 (t + T p) + 1, p < TF_RP, of every owned column.
+// three vectors.  Thread t owns rows 2 (t + T p), 2 (t + T p) + 1, p < RP = 1024 / (2 T), of every owned column.
 constexpr int TF_RS = 8;  // owned columns per CTA in registers
-constexpr int TF_RP = 2;  // row pairs per thread
+constexpr int TF_RROWS = 1024;  // rows covered by the register variant: row pairs per thread = TF_RROWS / (2 T)
 template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
 __global__ void __launch_bounds__(T, 1)
 trd_fused_kernel(const TfArgs a) {
@@ -132,12 +132,13 @@ trd_fused_kernel(const TfArgs a) {
       for (int r = tid; r < np; r += T) sAc[(size_t)s * np + r] = r < n ? src[r] : 0.0;
     }
   }
-  double2 ra[REGA ? TF_RS : 1][REGA ? TF_RP : 1];
+  constexpr int RP = REGA ? TF_RROWS / (2 * T) : 1;  // row pairs per thread (2 at T = 256, 1 at T = 512)
+  double2 ra[REGA ? TF_RS : 1][RP];
   if (REGA) {
 #pragma unroll
     for (int s = 0; s < TF_RS; ++s)
 #pragma unroll
-      for (int p = 0; p < TF_RP; ++p) {
+      for (int p = 0; p < RP; ++p) {
         const int c = g + s * G, r = 2 * (tid + T * p);
         double2 v = make_double2(0.0, 0.0);
         if (s < S && r < n) {
@@ -193,7 +194,7 @@ trd_fused_kernel(const TfArgs a) {
           vc[u] = u < S ? svn[c] : 0.0;
         }
 #pragma unroll
-        for (int p = 0; p < TF_RP; ++p) {
+        for (int p = 0; p < RP; ++p) {
           const int r = 2 * (tid + T * p);
           if (r + 1 >= first && r < np) {
             const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
@@ -503,7 +504,7 @@ trd_fused_kernel(const TfArgs a) {
 #pragma unroll
       for (int u = 0; u < TF_RS; ++u)
 #pragma unroll
-        for (int p = 0; p < TF_RP; ++p) {
+        for (int p = 0; p < RP; ++p) {
           const int c = g + u * G, r = 2 * (tid + T * p);
           if (u >= s0 && u < S) {
             const double2 x = ra[REGA ? u : 0][REGA ? p : 0];

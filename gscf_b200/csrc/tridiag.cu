@@ -669,7 +669,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   // columns in registers: <= 8 columns per CTA and <= 4 rows per thread (n = 1024 on 148 SMs)
   static int rega_ok = -1;
   if (rega_ok < 0) { const char* re = getenv("GSCF_B200_TF_REGA"); rega_ok = (re && re[0] == '0') ? 0 : 1; }
-  const bool rega = rega_ok && smem_a && !solo && !cluster && ceil_div(n, G) <= TF_RS && round_up(n, 2) <= 2 * 256 * TF_RP;
+  const bool rega = rega_ok && smem_a && !solo && !cluster && ceil_div(n, G) <= TF_RS && round_up(n, 2) <= TF_RROWS;
   const size_t smem = tf_smem_bytes(n, G, smem_a && !rega);
   static int t_big = -1;
   if (t_big < 0) { const char* tb = getenv("GSCF_B200_TF_TBIG"); t_big = tb ? atoi(tb) : 0; }
@@ -693,7 +693,12 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
       if (solo_t == 512) return tf_launch<1, true, 512, true>(a, G, cnt, false, smem, st);
       return tf_launch<1, true, 256, true>(a, G, cnt, false, smem, st);
     }
-    if (rega) return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
+    if (rega) {
+      static int rega_t = -1;
+      if (rega_t < 0) { const char* rt = getenv("GSCF_B200_TF_REGA_T"); rega_t = rt ? atoi(rt) : 256; }
+      if (rega_t == 512) return tf_launch<2, false, 512, false, true>(a, G, cnt, cluster, smem, st);
+      return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
+    }
     if (smem_a) {
       if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
