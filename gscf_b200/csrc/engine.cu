@@ -543,6 +543,12 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
     set_last_error("engine_create: invalid configuration");
     return GSCF_B200_ERR_INVALID_ARG;
   }
+  if ((long long)cfg->n_problems * cfg->n_blocks > 32768) {
+    // the batched kernels index the matrices of one launch with gridDim.y / .z (<= 65535)
+    set_last_error("engine_create: at most 32768 matrices (n_problems x n_blocks) per engine - shard larger "
+                   "ensembles over engines / GPUs (gscf_b200/ensemble.py)");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_last_error("no CUDA device: gscf_b200 has no CPU fallback");

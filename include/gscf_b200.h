@@ -186,7 +186,8 @@ typedef struct gscf_b200_engine gscf_b200_engine;
 
 typedef struct gscf_b200_config {
   int n_bas;
-  int n_problems;    /* P >= 1; P > 1 = batched ensemble (plain / DIIS) */
+  int n_problems;    /* P >= 1; P > 1 = batched ensemble in lock-step (all three solvers);
+                        P * n_blocks <= 32768 per engine */
   int n_blocks;      /* 1 restricted, 2 unrestricted (alpha/beta blocks) */
   int n_alpha;
   int n_beta;
