@@ -94,11 +94,6 @@ __global__ void gram_update_kernel(double* __restrict__ gram, int M, const doubl
   }
 }
 
-__global__ void scatter_orben_kernel(double* dst, const double* src, int n, const int* map, int cnt) {
-  // identity here (eigensolver already writes per-matrix); kept for interface symmetry
-  (void)dst; (void)src; (void)n; (void)map; (void)cnt;
-}
-
 // Upload the active lists.
 int upload_active(Engine* e) {
   std::vector<int> ap, am, ab[2];
@@ -126,7 +121,7 @@ int n_active(const Engine* e) {
   return c;
 }
 
-// Copy a set of n x n matrices (count of them) between host/device layouts.
+// ---- host <-> device matrix transfers ------------------------------------------------------------
 // `count` groups of `inner` consecutive matrices in ONE strided copy (an ensemble is thousands of small matrices: one
 // cudaMemcpy2DAsync each was 4096 x 3 launches per solve at C4).  Device side: group i at dev + i * dev_gstride, the
 // matrices of a group mstride = ld * n apart (so a group is inner * n rows of pitch ld); other side (host or device):

@@ -9,8 +9,8 @@
 // targets of the SCF need.  One-sided Jacobi needs a single n x n array (128 KiB at n = 128);
 // the two-sided form needs A and V (256 KiB > 227 KiB of shared memory per CTA).
 //
-// Used for: the batched ensemble eigensolves (BASELINE config 4, n = 128), the leaves of the
-// divide & conquer tridiagonal solver, and tiny problems (reference example, n = 14).
+// Used for: small problems (n <= 64 under EIG_AUTO: the reference example, n = 14) and, on request (EIG_JACOBI), batched
+// ensembles up to n = 160; the n = 128 ensemble of BASELINE config 4 runs faster through tridiagonalisation + D&C.
 #include "eig.cuh"
 
 namespace gscfb {

@@ -12,7 +12,7 @@
 //   dc_gather    non-deflated columns -> Gq, deflated columns/eigenvalues -> output; GEMM descriptors
 //   grouped DMMA GEMM  Q_top * U_top and Q_bot * U_bot with device-side sizes (after deflation)
 // Leaves (order <= 32 in batches, <= 16 for a few large matrices) are solved by dc_leaf_tql2_kernel: implicit QL
-// iteration, one warp per leaf.
+// iteration, one warp per leaf.  T is scaled to unit max-norm first (dc_scale_kernel), like dstedc.
 #include "stedc.cuh"
 
 #include "dc_core.hpp"
@@ -99,56 +99,6 @@ __global__ void dc_split_kernel(const double* __restrict__ d, const double* __re
       if (b == i + 1 || b == i) v -= fabs(eq[b - 1]);
     }
     dm[i] = v;
-  }
-}
-
-__global__ void dc_leaf_build_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
-                                     const int* __restrict__ map) {
-  const int leaf = blockIdx.x, zb = blockIdx.y;
-  const long long q = map ? map[zb] : zb;
-  const int n = ws.n, L = ws.L, lm = ws.lmax;
-  const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
-  const double* dm = ws.dmod + q * n;
-  const double* eq = e + q * dstride;
-  double* A = ws.leafA + ((size_t)zb * ws.nleaf + leaf) * lm * lm;
-  for (int idx = threadIdx.x; idx < lm * lm; idx += blockDim.x) {
-    const int c = idx / lm, r = idx - c * lm;
-    double v = 0.0;
-    if (r == c) v = r < m ? dm[lo + r] : dm[lo];  // padding: decoupled diagonal entry
-    else if (r == c + 1 && r < m) v = eq[lo + c];
-    A[idx] = v;
-  }
-}
-
-// Place the leaf eigenvectors into the block diagonal of Z0 and the eigenvalues into lam[0],
-// dropping the eigenpair of the padding entry (its vector is exactly e_last).
-__global__ void dc_leaf_scatter_kernel(StedcWs ws, double* __restrict__ Z0, int ldz, long long sZ,
-                                       const int* __restrict__ map) {
-  const int leaf = blockIdx.x, zb = blockIdx.y;
-  const long long q = map ? map[zb] : zb;
-  const int n = ws.n, L = ws.L, lm = ws.lmax;
-  const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
-  const double* Zl = ws.leafZ + ((size_t)zb * ws.nleaf + leaf) * lm * lm;
-  const double* Wl = ws.leafW + ((size_t)zb * ws.nleaf + leaf) * lm;
-  double* Zq = Z0 + q * sZ;
-  double* lam = ws.lam[0] + q * n;
-  __shared__ int s_skip;
-  if (threadIdx.x == 0) {
-    int skip = -1;
-    if (m < lm)
-      for (int j = 0; j < lm; ++j)
-        if (Zl[(size_t)j * lm + (lm - 1)] != 0.0) { skip = j; break; }
-    s_skip = skip;
-  }
-  __syncthreads();
-  const int skip = s_skip;
-  for (int idx = threadIdx.x; idx < m * lm; idx += blockDim.x) {
-    const int jsrc = idx / m, r = idx - jsrc * m;
-    if (jsrc == skip || jsrc >= lm) continue;
-    const int jdst = (skip >= 0 && jsrc > skip) ? jsrc - 1 : jsrc;
-    if (jdst >= m) continue;
-    Zq[(size_t)(lo + jdst) * ldz + lo + r] = Zl[(size_t)jsrc * lm + r];
-    if (r == 0) lam[lo + jdst] = Wl[jsrc];
   }
 }
 
@@ -297,7 +247,7 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
     sidx[r] = j;
   }
   __syncthreads();
-  __shared__ int s_K, s_nrot, s_c[4];
+  __shared__ int s_K, s_nrot;
   int* meta = ws.meta + ((size_t)q * ws.nleaf + t) * 8;
   int* gpos = ws.gpos + q * n + lo;
   int* rot_a = ws.rot_a + q * n + lo;
@@ -390,7 +340,7 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
         const int ty = sct[snd[p]];
         gpos[p] = ty == 1 ? o1++ : (ty == 2 ? o2++ : o3++);
       }
-      s_K = K; s_nrot = nrot; s_c[0] = c1; s_c[1] = c2; s_c[2] = c3;
+      s_K = K; s_nrot = nrot;
       meta[0] = K; meta[1] = nrot; meta[2] = c1; meta[3] = c2; meta[4] = c3;
       (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
     }
@@ -410,7 +360,7 @@ dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, i
     int o3 = c1 + (p_lo - o1);
     for (int pp = p_lo; pp < p_hi; ++pp) gpos[pp] = sct[snd[pp]] == 1 ? o1++ : o3++;
     if (tid == 0) {
-      s_K = Kp; s_nrot = 0; s_c[0] = c1; s_c[1] = 0; s_c[2] = Kp - c1;
+      s_K = Kp; s_nrot = 0;
       meta[0] = Kp; meta[1] = 0; meta[2] = c1; meta[3] = 0; meta[4] = Kp - c1;
       (ws.rho + (size_t)q * ws.nleaf)[t] = rho;
     }
@@ -641,9 +591,6 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
     ws.Zb = ws.S = ws.U = ws.Gq = nullptr;
     ws.Zb = (double*)take(mat);
   }
-  const size_t lsz = (size_t)cap * ws.nleaf * ws.lmax * ws.lmax * 8;
-  ws.leafA = (double*)take(lsz); ws.leafZ = (double*)take(lsz);
-  ws.leafW = (double*)take((size_t)cap * ws.nleaf * ws.lmax * 8);
   ws.descs = (GemmDesc*)take((size_t)cap * ws.nleaf * sizeof(GemmDesc));
   return off;
 }

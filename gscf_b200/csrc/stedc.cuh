@@ -34,9 +34,6 @@ struct StedcWs {
   double* U = nullptr;                  // [cap][ld*n] eigenvectors of the rank-one problems (transposed)
   double* Gq = nullptr;                 // [cap][ld*n] gathered non-deflated columns
   // scratch indexed by launch slot z
-  double* leafA = nullptr;              // [cap][nleaf][lmax*lmax]
-  double* leafZ = nullptr;              // [cap][nleaf][lmax*lmax]
-  double* leafW = nullptr;              // [cap][nleaf][lmax]
   GemmDesc* descs = nullptr;            // [cap][nleaf]  (2 per merge, <= nleaf/2 merges)
 };
 

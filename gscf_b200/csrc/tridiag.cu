@@ -369,10 +369,6 @@ __global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __r
   }
 }
 
-__global__ void copy_de_kernel(TrdWs ws, double* __restrict__ dout, double* __restrict__ eout, const int* map) {
-  (void)ws; (void)dout; (void)eout; (void)map;
-}
-
 }  // namespace
 }  // namespace gscfb
 #include "trd_panel.cuh"
