@@ -362,6 +362,15 @@ def run_ours(args, w):
                                            "traffic is the ncu figure of the first kernel only")
         flops_it = 7.0 * n ** 3 + 10.0 * n * n * na
         fp64_tf = flops_it * (iters_all / args.steps / world) * nblk / (dev_s / args.steps) / 1e12 if dev_s > 0 else 0.0
+        # FP64 roofline of the whole iteration: LAPACK-equivalent flops W_it = 7 n^3 + 10 n^2 o per rank
+        # against the DMMA peak measured on this GPU by a register-resident mma.sync.m8n8k4.f64 loop (outside the timed
+        # region; MEASURED_PEAKS.json only has bf16 and HBM)
+        dm, df, cp = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        fp64_roof = None
+        if L.lib.gscf_b200_measure_peaks(ctypes.byref(dm), ctypes.byref(df), ctypes.byref(cp)) == L.OK and dm.value > 0:
+            fp64_roof = {"bound": "tensor", "achieved": fp64_tf, "peak": dm.value, "unit": "TFLOP/s",
+                         "frac": fp64_tf / dm.value, "dfma_peak": df.value,
+                         "flops_per_iteration": flops_it * nblk, "scope": "whole SCF iteration, per GPU"}
         line = {
             "metric": "scf_iterations_per_s", "value": iters_all / dev_s, "unit": "iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
@@ -379,6 +388,7 @@ def run_ours(args, w):
                        "fp64_useful_tflops": fp64_tf, "problems_converged_per_s": conv_all / dev_s,
                        "energies_last_step": [float(x) for x in ensemble_table[:4, 0]]},
             "clocks": clocks,
+            "fp64_roofline": fp64_roof,
             "e2e": {"value": iters_all / e2e_s, "unit": "iterations/s",
                     "h2d_bytes_per_step": int((1 + nblk) * P_local * n * n * 8), "d2h_bytes_per_step": int(steps[-1]["d2h"])},
             "gpu_launches": int(launches_all),
