@@ -98,3 +98,23 @@ def test_scf_like_spectrum(dc):
     w, Z, st = dc(d, e, leaf=16)
     _check(d, e, w, Z)
     assert np.abs(w - np.linalg.eigvalsh(A)).max() < 1e-12
+
+
+@pytest.mark.parametrize("leaf", [8, 16, 32])
+def test_cascaded_noise_tridiagonal(dc, leaf):
+    """What the tridiagonalisation of a numerically low-rank matrix (all ones) hands to the solver: a 2 x 2 block of
+    norm n followed by blocks of noise whose magnitude drops by 1e-16 per block, down to 1e-176.  Deflation and the
+    secular solver must keep the eigenvectors orthogonal (the GPU path additionally flushes entries below 1e-140 of the
+    norm before its QL leaves: stedc.cu dc_scale_kernel)."""
+    rng = np.random.default_rng(leaf)
+    n = 96
+    mag = np.array([10.0 ** (-16 * (i // 8)) for i in range(n)])
+    d = rng.standard_normal(n) * mag
+    e = rng.standard_normal(n - 1) * mag[1:]
+    d[0], d[1], e[0] = 1.0, n - 1.0, np.sqrt(n - 1.0)
+    w, Z, st = dc(d, e, leaf=leaf)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    assert np.abs(Z.T @ Z - np.eye(n)).max() < 1e-13
+    assert np.abs(T @ Z - Z * w).max() < 1e-12 * n
+    wref = sla.eigh_tridiagonal(d, e, eigvals_only=True)
+    assert np.abs(np.sort(w) - wref).max() < 1e-12 * n
