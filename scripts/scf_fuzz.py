@@ -5,7 +5,7 @@ Gates: same iteration count, |dE| <= 1e-10, max |d eps| <= 1e-9 for every ensemb
 converge within max_iter must end with ERR_MAX_ITER on the GPU as well.  Cases whose decisive error norm lies within 0.5 %
 of the threshold are skipped (iteration parity is then a property of the rounding).
 
-usage: scf_fuzz.py [n_cases] [first_seed]
+usage: scf_fuzz.py [n_cases] [first_seed] [large]
 """
 import sys
 
@@ -27,7 +27,10 @@ def oracle_run(n, na, nb, aux, which, seed, **kw):
     return fn(p, F0, e1, e2, **kw)
 
 
-def main(n_cases=None, first=None):
+LARGE = [200, 257, 320, 400, 520]
+
+
+def main(n_cases=None, first=None, large=False):
     if n_cases is None:
         n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     if first is None:
@@ -35,7 +38,7 @@ def main(n_cases=None, first=None):
     bad = skipped = checked = 0
     for case in range(first, first + n_cases):
         rng = np.random.default_rng(1000 + case)
-        n = int(rng.choice([6, 9, 14, 20, 31, 32, 33, 48, 64, 65, 80, 96, 130, 150]))
+        n = int(rng.choice(LARGE if large else [6, 9, 14, 20, 31, 32, 33, 48, 64, 65, 80, 96, 130, 150]))
         na = int(rng.integers(1, max(2, n // 4)))
         nb = na if rng.random() < 0.6 else int(rng.integers(1, na + 1))
         aux = int(rng.integers(2, 10))
@@ -43,6 +46,8 @@ def main(n_cases=None, first=None):
         m = int(rng.integers(1, 9))
         P = int(rng.choice([1, 1, 2, 5]))
         eig = int(rng.choice([L.EIG_AUTO, L.EIG_JACOBI, L.EIG_TRIDIAG_DC])) if n <= 150 else L.EIG_AUTO
+        if large:
+            P = min(P, 2)
         thr = 1e-5 if which == "toda" else float(rng.choice([5e-7, 1e-6, 1e-8]))
         max_iter = 40
         params = {"max_error_norm": thr, "max_iter": max_iter}
@@ -102,4 +107,4 @@ def main(n_cases=None, first=None):
 
 
 if __name__ == "__main__":
-    sys.exit(1 if main()[0] else 0)
+    sys.exit(1 if main(large=len(sys.argv) > 3 and sys.argv[3] == "large")[0] else 0)
