@@ -379,17 +379,25 @@ struct IterScalars {
   std::vector<int> fail, eiginfo;
 };
 
-// One D2H round trip per iteration: dots, energies, failure flags.
-int fetch_scalars(Engine* e, IterScalars& s) {
-  s.dots.resize((size_t)e->P * kMaxHistory);
-  s.energies.resize((size_t)e->P * 2);
-  s.fail.resize(e->P);
-  s.eiginfo.resize((size_t)e->P * e->nblk);
-  GSCF_CUDA_TRY(cudaMemcpyAsync(s.dots.data(), e->dots, s.dots.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  GSCF_CUDA_TRY(cudaMemcpyAsync(s.energies.data(), e->energies, s.energies.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  GSCF_CUDA_TRY(cudaMemcpyAsync(s.fail.data(), e->fail, s.fail.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  GSCF_CUDA_TRY(cudaMemcpyAsync(s.eiginfo.data(), e->eiginfo, s.eiginfo.size() * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+// One D2H round trip per iteration: dots, energies, failure flags (and the DIIS coefficients when asked for), through
+// pinned staging buffers - into pageable memory every cudaMemcpyAsync is its own blocking transfer (~15 us each, five per
+// iteration: 1 % of a C2 iteration).
+int fetch_scalars(Engine* e, IterScalars& s, double* coeff_out = nullptr) {
+  const size_t nd = (size_t)e->P * kMaxHistory, ne = (size_t)e->P * 2, nf = (size_t)e->P, ni = (size_t)e->P * e->nblk;
+  double* hd = e->h_stage;           // [nd] dots | [ne] energies | [nd] coefficients
+  int* hi = e->h_istage;             // [nf] fail | [ni] eiginfo
+  GSCF_CUDA_TRY(cudaMemcpyAsync(hd, e->dots, nd * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GSCF_CUDA_TRY(cudaMemcpyAsync(hd + nd, e->energies, ne * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (coeff_out)
+    GSCF_CUDA_TRY(cudaMemcpyAsync(hd + nd + ne, e->coeff, nd * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  GSCF_CUDA_TRY(cudaMemcpyAsync(hi, e->fail, nf * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  GSCF_CUDA_TRY(cudaMemcpyAsync(hi + nf, e->eiginfo, ni * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   GSCF_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  s.dots.assign(hd, hd + nd);
+  s.energies.assign(hd + nd, hd + nd + ne);
+  s.fail.assign(hi, hi + nf);
+  s.eiginfo.assign(hi + nf, hi + nf + ni);
+  if (coeff_out) std::copy(hd + nd + ne, hd + nd + ne + nd, coeff_out);
   return GSCF_B200_OK;
 }
 
@@ -607,6 +615,12 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
   A(&e->eiginfo, PM);
   A(&e->act_p, P);
   A(&e->keep_p, P);
+  if (st == GSCF_B200_OK &&
+      (cudaMallocHost((void**)&e->h_stage, (P * (2 * kMaxHistory + 2)) * sizeof(double)) != cudaSuccess ||
+       cudaMallocHost((void**)&e->h_istage, (P + PM) * sizeof(int)) != cudaSuccess)) {
+    set_last_error("cudaMallocHost failed");
+    st = GSCF_B200_ERR_CUDA;
+  }
   A(&e->act_m, PM);
   A(&e->act_mb[0], P);
   A(&e->act_mb[1], P);
@@ -652,6 +666,7 @@ void gscf_b200_engine_destroy(gscf_b200_engine* e) {
   cudaFree(e->energies); cudaFree(e->scal); cudaFree(e->fail); cudaFree(e->eiginfo);
   cudaFree(e->eigwork); cudaFree(e->mdwork); cudaFree(e->act_p); cudaFree(e->keep_p); cudaFree(e->act_m);
   cudaFree(e->act_mb[0]); cudaFree(e->act_mb[1]);
+  cudaFreeHost(e->h_stage); cudaFreeHost(e->h_istage);
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->owns_stream && e->stream) cudaStreamDestroy(e->stream);
   delete e;
@@ -954,9 +969,7 @@ int gscf_b200_solve_diis(gscf_b200_engine* e, const gscf_b200_params* prm) {
         GSCF_CHECK_LAUNCH();
       }
       e->last_error_slot = slot;
-      if (k >= 2)
-        GSCF_CUDA_TRY(cudaMemcpyAsync(hcoeff.data(), e->coeff, hcoeff.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-      GSCF_TRY(fetch_scalars(e, sc));
+      GSCF_TRY(fetch_scalars(e, sc, k >= 2 ? hcoeff.data() : nullptr));
       if (k == 1) for (int p : act) hcoeff[(size_t)p * kMaxHistory] = 1.0;
       absorb_scalars(e, sc, 0, k >= 2);
       for (int p : act) record_trace(e, p, hcoeff.data() + (size_t)p * kMaxHistory, k);

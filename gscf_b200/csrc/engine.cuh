@@ -50,8 +50,8 @@ struct gscf_b200_engine {
   int* act_m = nullptr;     // active matrices (p*nblk+b)
   int* act_mb[2] = {nullptr, nullptr};
   // pinned host staging
-  double* h_stage = nullptr;  // [P * (kMaxHistory + 2 + 4)]
-  int* h_istage = nullptr;    // [P * 3]
+  double* h_stage = nullptr;  // [P * (2 kMaxHistory + 2)]: dots | energies | coefficients
+  int* h_istage = nullptr;    // [P * (1 + nblk)]: DIIS failure flags | eigensolver info
 
   // ---- host mirrors --------------------------------------------------------------------------
   int cur = 0;  // index of the current coefficient buffer in Cbuf/orben
