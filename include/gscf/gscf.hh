@@ -320,8 +320,8 @@ struct ScfBase<State>::Driver {
   size_t n = 0;
   int n_occ = 0;
   int mirrored_iter = -1;
-  std::exception_ptr error;
-  Method method;
+  std::exception_ptr error = nullptr;
+  Method method = Method::Plain;
 
   static void check(int st) {
     if (st != GSCF_B200_OK) throw b200::Error(st, gscf_b200_last_error());
