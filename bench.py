@@ -148,6 +148,14 @@ def run_reference(args, w):
     if rank != 0:
         return
     cores = os.cpu_count()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: give LAPACK / BLAS every host core back (the arm is "the reference's
+    # CPU path with all the host threads it can use"; the other ranks have already returned)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:  # noqa: BLE001
+        pass
     sample_iters = 3 if w["n"] >= 1024 else 6
     sample = f"{sample_iters} DIIS iterations of one {w['desc']} problem per step (BLAS threads = all cores)"
     times, iters = [], []
