@@ -143,6 +143,43 @@ def oracle_time_solve(w, seed, max_iter=None):
     return n_iter, total - fock_t[0], fock_t[0], energy
 
 
+def _pool_worker(job):
+    """One ensemble member on one core (BLAS threads = 1); returns (n_iter, scf_path_seconds)."""
+    try:
+        import scipy.linalg  # noqa: F401  (load its OpenBLAS before limiting the pools)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        pass
+    w, seed, max_iter = job
+    n_it, t_scf, _, _ = oracle_time_solve(w, seed=seed, max_iter=max_iter)
+    return n_it, t_scf
+
+
+def oracle_time_ensemble(w, seeds, max_iter=None):
+    """CPU baseline of an ensemble workload: one problem per core, BLAS threads = 1, all cores busy.
+    Returns (iterations/s aggregated over the cores, cores, members solved)."""
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")  # the parent may hold a CUDA context: never fork it
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"  # inherited by the workers
+    try:
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_pool_worker, [(dict(w), int(s), max_iter) for s in seeds], chunksize=1)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    its = sum(r[0] for r in res)
+    busy = sum(r[1] for r in res)          # core-seconds spent in the SCF path while every core was loaded
+    return its / (busy / cores), cores, len(res), its
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -156,15 +193,27 @@ def run_reference(args, w):
         threadpool_limits(limits=cores)
     except Exception:  # noqa: BLE001
         pass
-    sample_iters = 3 if w["n"] >= 1024 else 6
-    sample = f"{sample_iters} DIIS iterations of one {w['desc']} problem per step (BLAS threads = all cores)"
-    times, iters = [], []
-    for s in range(args.warmup + args.steps):
-        n_it, t_scf, t_fock, _ = oracle_time_solve(w, seed=0, max_iter=sample_iters)
-        if s >= args.warmup:
-            times.append(t_scf)
-            iters.append(n_it)
-    value = sum(iters) / sum(times)
+    if w["P"] > 1:
+        # ensembles: one member per core; every step solves 2 members per core completely
+        vals, times, iters = [], [], []
+        for s in range(args.warmup + args.steps):
+            v, cores, nmem, its = oracle_time_ensemble(w, range(2 * cores))
+            if s >= args.warmup:
+                vals.append(v)
+                iters.append(its)
+                times.append(its / v)  # SCF-path wall time of the step with every core busy
+        value = sum(iters) / sum(times)
+        sample = f"{2 * cores} members of {w['desc']} per step, one per core (BLAS threads = 1), full DIIS solves"
+    else:
+        sample_iters = 3 if w["n"] >= 1024 else 6
+        sample = f"{sample_iters} DIIS iterations of one {w['desc']} problem per step (BLAS threads = all cores)"
+        times, iters = [], []
+        for s in range(args.warmup + args.steps):
+            n_it, t_scf, t_fock, _ = oracle_time_solve(w, seed=0, max_iter=sample_iters)
+            if s >= args.warmup:
+                times.append(t_scf)
+                iters.append(n_it)
+        value = sum(iters) / sum(times)
     line = {
         "impl": "reference", "metric": "scf_iterations_per_s", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -409,6 +458,13 @@ def run_ours(args, w):
                                     "sample": f"1 full DIIS solve ({n_it} iterations) of problem seed {seeds[0]} on the host "
                                               f"(oracle/: LAPACK dsygvd + dgemm, all BLAS threads); Fock builder excluded",
                                     "energy_abs_diff_vs_gpu": abs(e_ref - float(steps[-1]["e"][0]))}
+            if ensemble:
+                # an ensemble's CPU baseline is one member per core, not one member on all cores
+                v, cores, nmem, _ = oracle_time_ensemble(w, seeds[:2 * (os.cpu_count() or 1)])
+                line["cpu_baseline"].update({
+                    "value": v, "cores": cores, "single_problem_all_threads": n_it / t_scf,
+                    "sample": f"{nmem} members (seeds {seeds[0]}..{seeds[nmem - 1]}), full DIIS solves, one member per core "
+                              f"with BLAS threads = 1 (oracle/: LAPACK dsygvd + dgemm); Fock builder excluded"})
         print(json.dumps(line))
     eng.close()
     fock.close()
