@@ -360,3 +360,19 @@ def test_syev_nan_input_is_contained(env, n, method):
     for b in range(1, batch):
         assert flags[b] == 0
         assert np.abs(w[b] - wref).max() < 1e-12 * n * max(1.0, np.abs(wref).max())
+
+
+def test_dgemm_randomised_sweep(env):
+    """60 random shapes around the tile edges, all transposes, odd leading dimensions, batches, beta = 0 on NaN-filled C
+    (scripts/gemm_fuzz.py)."""
+    from scripts.gemm_fuzz import main
+
+    assert main(60, 500) == 0
+
+
+def test_generalised_eigenproblem_conditioning(env):
+    """H C = S C eps through the public solver API for overlaps of condition 3 .. 1e8 (scripts/geneig_fuzz.py): errors
+    bounded by what the conditioning allows, C^T S C = I."""
+    from scripts.geneig_fuzz import main
+
+    assert main(12, 100) == 0
