@@ -75,6 +75,8 @@ int gscf_b200_dgemm(int transa, int transb, int m, int n, int k, double alpha, c
 
 /* Symmetric eigensolver, all pairs ascending: A (n x n, lower triangle read, destroyed) ->
  * w[n], Z (n x n, orthonormal columns).  batch matrices with the given strides.
+ * Like dsyev, a matrix whose max-norm is outside [1e-100, 1e100] is scaled internally;
+ * info[q] != 0 reports non-finite input or a failed reduction of matrix q.
  * work: device workspace of gscf_b200_syev_worksize(n, batch, method) bytes. */
 size_t gscf_b200_syev_worksize(int n, int batch, int method);
 int gscf_b200_syev(int method, int n, double* A, int lda, long long strideA, double* w,
