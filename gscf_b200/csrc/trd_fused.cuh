@@ -63,6 +63,15 @@ __device__ __forceinline__ void tf_st2(double* p, double x, double y) {
 // offset of entry r inside a step's chunked exchange slot (see the kernel)
 // release fence of the exchange: acq_rel at gpu scope (a `__threadfence()` is the stronger fence.sc)
 __device__ __forceinline__ void tf_fence_release() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// arrive at the exchange counter: release fence + relaxed add, or (GSCF_TF_RED_RELEASE) one red.release.gpu
+__device__ __forceinline__ void tf_arrive(unsigned* ctr) {
+#ifdef GSCF_TF_RED_RELEASE
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#else
+  tf_fence_release();
+  atomicAdd(ctr, 1u);
+#endif
+}
 __device__ __forceinline__ unsigned tf_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -400,11 +409,10 @@ trd_fused_kernel(const TfArgs a) {
 #ifdef GSCF_TF_DEBUG_TIMING
           const long long tf0 = clock64();
 #endif
-          tf_fence_release();
+          tf_arrive(ctr);
 #ifdef GSCF_TF_DEBUG_TIMING
           tfence += clock64() - tf0;
 #endif
-          atomicAdd(ctr, 1u);
           const unsigned target = (unsigned)G * (unsigned)(j + 1);
           if (*reinterpret_cast<volatile unsigned*>(a.abort_flag) == 0u) {
             const long long t0 = clock64();
