@@ -71,3 +71,30 @@ def test_genmap_and_control_params():
     assert t.min_fock_prefactor == 0.1 and t.n_prev_steps == 2 and t.max_error_norm == 5e-7
     assert G.PulayDiisScfKeys.n_prev_steps == "diis_n_prev_steps"
     assert G.TruncatedOptDampScfKeys.n_prev_steps == "toda_n_prev_steps"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (-pedantic) and a C host must link against the library
+    (host-only entry points here: default parameters and the TODA line search, TruncatedOptDampScf.hh:370-394)."""
+    import subprocess
+
+    src = tmp_path / "c_host.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "gscf_b200.h"\n'
+        "int main(void) {\n"
+        "  gscf_b200_params p;\n"
+        "  gscf_b200_default_params(&p);\n"
+        "  if (p.max_iter != 100 || p.diis_n_prev_steps != 4 || p.toda_n_prev_steps != 2) return 1;\n"
+        "  if (p.max_error_norm != 5e-7 || p.toda_min_fock_prefactor != 0.05) return 2;\n"
+        "  /* s < 0, c > 0: interior minimum -s / (2 c) = 0.25 */\n"
+        "  if (gscf_b200_compute_damping_coeff(-1.0, 2.0, 0.05) != 0.25) return 3;\n"
+        "  /* descent direction lost (s >= 0): full step like the reference */\n"
+        "  if (gscf_b200_compute_damping_coeff(1.0, 2.0, 0.05) != 1.0) return 4;\n"
+        '  printf("%s\\n", gscf_b200_last_error() ? "ok" : "null");\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "c_host"
+    libdir = os.path.join(ROOT, "gscf_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-L", libdir, "-lgscf_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
