@@ -30,6 +30,7 @@ from .scf import (  # noqa: F401
     pulay_diis_scf,
     truncated_opt_damp_scf,
     generalised_eigh,
+    eig_driver,
     pulay_error,
     compute_damping_coeff,
     diis_linear_system_matrix,

@@ -63,14 +63,42 @@ class ScfResult:
 # --------------------------------------------------------------------------------------
 # building blocks of ScfBase
 # --------------------------------------------------------------------------------------
+_EIG_DRIVER = "gvd"
+
+
+class eig_driver:
+    """Context manager selecting the LAPACK route of ``generalised_eigh`` (test infrastructure: used to show how far two
+    LAPACK builds of the *same* algorithm drift apart, tests/test_toda_sensitivity_cpu.py).  ``gvd`` (default, divide &
+    conquer ``dsygvd``), ``gv`` (QR iteration ``dsygv``), ``loewdin`` (X = S^-1/2, ``dsyevd`` of X F X)."""
+
+    def __init__(self, name: str):
+        assert name in ("gvd", "gv", "loewdin"), name
+        self.name = name
+
+    def __enter__(self):
+        global _EIG_DRIVER
+        self.saved, _EIG_DRIVER = _EIG_DRIVER, self.name
+        return self
+
+    def __exit__(self, *exc):
+        global _EIG_DRIVER
+        _EIG_DRIVER = self.saved
+        return False
+
+
 def generalised_eigh(F: np.ndarray, S: np.ndarray):
     """F C = S C eps, all pairs, ascending, C^T S C = I.
 
     ``src/gscf/ScfBase.hh:291-339`` delegates to lazyten's EigensystemSolver
     (dense: armadillo/LAPACK generalised symmetric solver); restated with
-    LAPACK ``dsygvd``.
+    LAPACK ``dsygvd`` (other routes only through ``eig_driver``).
     """
-    w, v = sla.eigh(F, S, driver="gvd", check_finite=False)
+    if _EIG_DRIVER == "loewdin":
+        ws, U = np.linalg.eigh(S)
+        X = (U * ws**-0.5) @ U.T
+        w, Z = np.linalg.eigh(X @ F @ X)
+        return w, X @ Z
+    w, v = sla.eigh(F, S, driver=_EIG_DRIVER, check_finite=False)
     return w, v
 
 
