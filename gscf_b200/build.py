@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libgscf_b200.so")
 SOURCES = ["gemm.cu", "stream.cu", "jacobi.cu", "eig.cu", "tridiag.cu", "stedc.cu", "chol.cu", "fock_df.cu",
-           "engine.cu", "capi.cu"]
+           "engine.cu", "gather.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr",
@@ -55,7 +55,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(LIB, objs):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                      "-lcudart_static", "-Xcompiler", "-fPIC"]
+                                                      "-lcudart_static", "-ldl", "-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

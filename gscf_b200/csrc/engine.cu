@@ -196,8 +196,9 @@ int call_hook(Engine* e, int ev, int it) {
 
 // ---- path steps ------------------------------------------------------------------------------
 
-// Generalised eigensolve of the matrices at Fd (+p*fd_pstride + b*mstride) for the active set:
-//   A' = X Fd X (X = S^-1/2 symmetric), A' Z = Z w, C = X Z.      ScfBase.hh:291-339
+// Generalised eigensolve of the matrices at Fd (+p*fd_pstride + b*mstride) for the active set (ScfBase.hh:291-339):
+//   default (Cholesky, S = L L^T, X = L^-1 lower triangular):  A' = X Fd X^T,  A' Z = Z w,  C = X^T Z
+//   GSCF_B200_ORTHO=loewdin (X = S^-1/2 symmetric):            A' = X Fd X,    A' Z = Z w,  C = X Z
 int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact) {
   Span sp(e, PH_EIG);
   const int n = e->n, ld = e->ld;
@@ -493,8 +494,11 @@ int absorb_scalars(Engine* e, const IterScalars& s, int self_index, bool diis_fl
       e->status[p] = GSCF_B200_ERR_DIIS_STEP;  // ExcDiisStepFailed
       e->active[p] = 0;
     }
-    if (e->active[p] && !std::isfinite(e->errnorm[p]) ) {
-      // non-finite error: the inner solvers produced garbage
+    if (e->active[p] && !std::isfinite(e->errnorm[p]) && !e->error_host) {
+      // non-finite built-in Pulay error: the inner solvers produced garbage.  With a HOST error function a non-finite
+      // norm is the caller's business: the default residual error returns Constants<>::invalid on the first iteration
+      // (ScfBase.hh:271-275), which only means "not converged" (ScfBase.hh:123-126) - real eigensolver failures are
+      // still caught by eiginfo above.
       e->status[p] = GSCF_B200_ERR_EIGENSOLVER;
       e->active[p] = 0;
     }
@@ -1191,6 +1195,16 @@ int gscf_b200_get_density(gscf_b200_engine* e, double* D, int ld) {
 int gscf_b200_get_error(gscf_b200_engine* e, double* E, int ld) {
   if (!e || !E || ld < e->n || e->last_error_slot < 0) return GSCF_B200_ERR_INVALID_ARG;
   return copy_out(e, E, ld, e->Eslot(e->last_error_slot), e->ering_pstride(), e->mstride);
+}
+int gscf_b200_get_history_size(gscf_b200_engine* e) { return e ? (int)e->hist_order.size() : -1; }
+// ring entry i (oldest = 0) of the error / problem-matrix history (PulayDiisScfState::errors :60, prev_problem_matrix_ptrs :56)
+int gscf_b200_get_error_entry(gscf_b200_engine* e, int entry, double* E, int ld) {
+  if (!e || !E || ld < e->n || entry < 0 || entry >= (int)e->hist_order.size()) return GSCF_B200_ERR_INVALID_ARG;
+  return copy_out(e, E, ld, e->Eslot(e->hist_order[entry]), e->ering_pstride(), e->mstride);
+}
+int gscf_b200_get_fock_entry(gscf_b200_engine* e, int entry, double* F, int ld) {
+  if (!e || !F || ld < e->n || entry < 0 || entry >= (int)e->hist_order.size()) return GSCF_B200_ERR_INVALID_ARG;
+  return copy_out(e, F, ld, e->Fslot(e->hist_order[entry]), e->fring_pstride(), e->mstride);
 }
 int gscf_b200_get_diis_coefficients(gscf_b200_engine* e, double* c, int* n_coeff) {
   if (!e || !c || !n_coeff) return GSCF_B200_ERR_INVALID_ARG;

@@ -23,7 +23,7 @@ struct gscf_b200_engine {
 
   // ---- device state ------------------------------------------------------------------------
   double* S = nullptr;      // [P*nblk] (or 1 if shared) overlap
-  double* X = nullptr;      // same shape: S^-1/2
+  double* X = nullptr;      // same shape: the orthogonaliser (L^-1, or S^-1/2 with GSCF_B200_ORTHO=loewdin)
   long long sx_stride = 0;  // 0 when shared
   double* Fring = nullptr;  // [P][M+1][nblk] problem matrices (slot M: initial matrix)
   double* Ering = nullptr;  // [P][M][nblk] error matrices

@@ -62,26 +62,96 @@ def summarise(records: np.ndarray) -> Dict[str, float]:
     }
 
 
-def solve_ensemble(n_bas, n_alpha, n_beta=None, n_aux=None, n_problems=1, seeds: Optional[List[int]] = None,
-                   method="diis", params=None, group=None):
-    """Solve this rank's shard of a synthetic DF ensemble on its GPU and gather the records.
+class NcclGather:
+    """The C-ABI collective (gscf_b200_comm_* / gscf_b200_ensemble_gather, include/gscf_b200.h section 3b) driven from
+    a torch.distributed job: rank 0 creates the NCCL unique id, torch.distributed only carries those 128 bytes to the
+    other ranks; the gather itself is the library's own ncclAllGather on the engine's stream."""
 
-    Returns (records of all problems in problem order, local Engine closed)."""
-    import torch.distributed as dist
+    def __init__(self, group=None):
+        import ctypes as C
 
-    from . import lib as L
+        import torch
+        import torch.distributed as dist
+
+        from . import lib as L
+
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            L.check(L.lib.gscf_b200_comm_unique_id(buf))
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+            dist.broadcast(t, src=0, group=group)
+            buf = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        self.handle = C.c_void_p()
+        L.check(L.lib.gscf_b200_comm_create(buf, self.world, self.rank, C.byref(self.handle)))
+
+    def gather(self, engine, n_problems: int) -> np.ndarray:
+        """Records of all problems in problem order (P x 5, RECORD_FIELDS); `engine` holds this rank's shard."""
+        import ctypes as C
+
+        from . import lib as L
+
+        counts = (C.c_int * self.world)(*[hi - lo for lo, hi in (shard_range(n_problems, r, self.world)
+                                                                    for r in range(self.world))])
+        out = (L.Record * n_problems)()
+        L.check(L.lib.gscf_b200_ensemble_gather(engine.handle, self.handle, counts, out))
+        return np.array([[r.energy_total, r.error_norm, r.n_iter, r.converged, r.status] for r in out], dtype=float
+                        ).reshape(n_problems, len(RECORD_FIELDS))
+
+    def close(self):
+        from . import lib as L
+
+        if self.handle:
+            L.lib.gscf_b200_comm_destroy(self.handle)
+            self.handle = None
+
+
+def _solve_shard_on_gpu(n_bas, n_alpha, n_beta, n_aux, seeds, method, params):
     from .solvers import DeviceDFFock, solve_device_problem
+
+    fock = DeviceDFFock(n_bas, n_alpha, n_beta, n_aux=n_aux, seeds=seeds)
+    eng = None
+    try:
+        eng, st = solve_device_problem(fock, method, params)
+        e1, e2 = eng.energies()
+        return pack_records(e1 + e2, eng.error_norm(), eng.n_iter(), eng.converged(), eng.status())
+    finally:
+        if eng is not None:
+            eng.close()
+        fock.close()
+
+
+def solve_ensemble(n_bas, n_alpha, n_beta=None, n_aux=None, n_problems=1, seeds: Optional[List[int]] = None,
+                   method="diis", params=None, group=None, local_solver=None):
+    """Solve this rank's shard of a synthetic DF ensemble on its GPU and gather the records of all problems (problem
+    order).  Every rank reaches the collective exactly once: a rank whose shard is empty (more ranks than problems)
+    contributes zero records, and a rank whose local solve raises contributes records with status -1 and re-raises
+    after the gather, so the other ranks never hang in it.  `local_solver(seeds) -> records` replaces the GPU solve
+    (host-logic tests)."""
+    import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_range(n_problems, rank, world)
     all_seeds = list(range(n_problems)) if seeds is None else list(seeds)
-    fock = DeviceDFFock(n_bas, n_alpha, n_beta, n_aux=n_aux, seeds=all_seeds[lo:hi])
-    eng, st = solve_device_problem(fock, method, params)
-    try:
-        e1, e2 = eng.energies()
-        local = pack_records(e1 + e2, eng.error_norm(), eng.n_iter(), eng.converged(), eng.status())
-    finally:
-        eng.close()
-        fock.close()
-    return gather_records(local, n_problems, group)
+    failure = None
+    if hi == lo:
+        local = np.zeros((0, len(RECORD_FIELDS)))
+    else:
+        try:
+            if local_solver is not None:
+                local = np.asarray(local_solver(all_seeds[lo:hi]), dtype=float)
+            else:
+                local = _solve_shard_on_gpu(n_bas, n_alpha, n_beta, n_aux, all_seeds[lo:hi], method, params)
+        except Exception as exc:  # noqa: BLE001 - the collective below must still be reached
+            failure = exc
+            local = np.zeros((hi - lo, len(RECORD_FIELDS)))
+            local[:, 1] = np.nan
+            local[:, 4] = -1.0
+    records = gather_records(local, n_problems, group)
+    if failure is not None:
+        raise failure
+    return records

@@ -48,6 +48,11 @@ class FockArgs(C.Structure):
                 ("F_problem_stride", C.c_longlong), ("energies_out", C.c_void_p), ("stream", C.c_void_p)]
 
 
+class Record(C.Structure):
+    _fields_ = [("energy_total", C.c_double), ("error_norm", C.c_double), ("n_iter", C.c_int),
+                ("converged", C.c_int), ("status", C.c_int), ("reserved", C.c_int)]
+
+
 FOCK_DEVICE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FockArgs))
 FOCK_HOST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double),
                            C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -111,6 +116,14 @@ SIGNATURES = {
     "gscf_b200_get_diagmat": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_density": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_error": (C.c_int, [_P, _D, C.c_int]),
+    "gscf_b200_get_history_size": (C.c_int, [_P]),
+    "gscf_b200_get_error_entry": (C.c_int, [_P, C.c_int, _D, C.c_int]),
+    "gscf_b200_get_fock_entry": (C.c_int, [_P, C.c_int, _D, C.c_int]),
+    "gscf_b200_nccl_version": (C.c_int, []),
+    "gscf_b200_comm_unique_id": (C.c_int, [_P]),
+    "gscf_b200_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gscf_b200_comm_destroy": (None, [_P]),
+    "gscf_b200_ensemble_gather": (C.c_int, [_P, _P, _I, _P]),
     "gscf_b200_get_diis_coefficients": (C.c_int, [_P, _D, _I]),
     "gscf_b200_get_current_diis_coefficients": (C.c_int, [_P, _D, C.c_int]),
     "gscf_b200_get_error_overlaps": (C.c_int, [_P, C.c_int, C.c_int, _D, _I]),

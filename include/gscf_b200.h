@@ -216,7 +216,8 @@ void gscf_b200_engine_destroy(gscf_b200_engine* e);
 void* gscf_b200_engine_stream(gscf_b200_engine* e);
 
 /* Overlap (ScfStateBase.hh:175): n x n (ld) per problem (or one if shared_overlap); the
- * orthogonaliser X = S^-1/2 is factorised once here. */
+ * orthogonaliser is factorised once here: Cholesky S = L L^T, X = L^-1 by default, the Loewdin
+ * X = S^-1/2 with the environment variable GSCF_B200_ORTHO=loewdin. */
 int gscf_b200_set_overlap(gscf_b200_engine* e, const double* S, int ld, int memloc);
 int gscf_b200_set_fock_builder_device(gscf_b200_engine* e, gscf_b200_fock_device_fn fn, void* ctx);
 int gscf_b200_set_fock_builder_host(gscf_b200_engine* e, gscf_b200_fock_host_fn fn, void* ctx);
@@ -268,6 +269,12 @@ int gscf_b200_get_diis_coefficients(gscf_b200_engine* e, double* c, int* n_coeff
 /* Coefficients of the extrapolation being diagonalised right now (valid inside the NEW_DIAGMAT /
  * UPDATE_EIGENPAIRS hooks), [P][k] oldest -> newest. */
 int gscf_b200_get_current_diis_coefficients(gscf_b200_engine* e, double* c, int k);
+/* Lazy materialisation of the DIIS rings (PulayDiisScfState :56-81) after a solve - a host that overrides no hook
+ * never pays a per-iteration device-to-host copy: number of entries in the rings, then entry i (oldest = 0) of the
+ * error ring / of the problem-matrix ring, [P][n_blocks] n x n each. */
+int gscf_b200_get_history_size(gscf_b200_engine* e);
+int gscf_b200_get_error_entry(gscf_b200_engine* e, int entry, double* E, int ld);
+int gscf_b200_get_fock_entry(gscf_b200_engine* e, int entry, double* F, int ld);
 /* overlap vector of ring entry i (oldest = 0), newest-first like PulayDiisScf.hh:67-70 */
 int gscf_b200_get_error_overlaps(gscf_b200_engine* e, int problem, int entry, double* ov, int* len);
 int gscf_b200_get_damping_coeff(gscf_b200_engine* e, double* damp);    /* TODA, [P] */
@@ -284,6 +291,34 @@ int gscf_b200_get_timings(gscf_b200_engine* e, double* scf_ms, double* fock_ms);
  * [14] Fock builder inside the last gscf_b200_set_guess. */
 int gscf_b200_get_phase_timings(gscf_b200_engine* e, double* ms, int n);
 int gscf_b200_set_phase_timing(gscf_b200_engine* e, int enabled);
+
+/* ======================================================================================
+ * 3b. Sharded ensembles: one process per GPU, the ensemble split by problem index,
+ *     no data-path collective; the ONLY collective is this all-gather of per-problem records
+ *     (NCCL over NVLink, bound at run time with dlopen("libnccl.so.2") - no link-time
+ *     dependency).  The reference has no counterpart.
+ *     Host protocol: rank 0 calls gscf_b200_comm_unique_id and distributes the 128 bytes by its own
+ *     means (MPI_Bcast, a file, torch.distributed ...); every rank calls gscf_b200_comm_create with
+ *     the CUDA device of its engine current; after the solve every rank calls
+ *     gscf_b200_ensemble_gather with counts[r] = problems owned by rank r.
+ * ====================================================================================== */
+typedef struct gscf_b200_comm gscf_b200_comm;
+typedef struct gscf_b200_record {
+  double energy_total;   /* E_1e + E_2e of the final problem matrix */
+  double error_norm;     /* last_error_norm */
+  int n_iter;
+  int converged;
+  int status;            /* gscf_b200_status of the problem */
+  int reserved;
+} gscf_b200_record;
+int gscf_b200_nccl_version(void);  /* 0 when no NCCL library can be loaded */
+int gscf_b200_comm_unique_id(void* id128);
+int gscf_b200_comm_create(const void* id128, int world, int rank, gscf_b200_comm** out);
+void gscf_b200_comm_destroy(gscf_b200_comm* c);
+/* out: sum(counts) records on the host, ordered by rank then local problem index - identical on
+ * every rank.  Runs on the engine's stream; returns after the records are on the host. */
+int gscf_b200_ensemble_gather(gscf_b200_engine* e, gscf_b200_comm* c, const int* counts,
+                              gscf_b200_record* out);
 
 /* ======================================================================================
  * 4. Synthetic density-fitted Fock builder (device plugin used by bench.py and the tests;

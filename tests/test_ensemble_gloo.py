@@ -65,3 +65,48 @@ def test_shard_range_partitions():
     s = summarise(np.array([[-1.0, 1e-8, 5, 1, 0], [-2.0, 1e-3, 100, 0, 5]]))
     assert s == {"n_problems": 2, "n_converged": 1, "iterations_total": 105, "iterations_max": 100,
                  "iterations_mean": 52.5}
+
+
+def _worker_solve(rank, world, port, n_problems, out, fail_rank):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from gscf_b200 import ensemble
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def fake(seeds):
+        if rank == fail_rank:
+            raise RuntimeError("local solve failed")
+        idx = np.asarray(seeds)
+        return ensemble.pack_records(-1.0 * idx, 1e-8 + 0 * idx, 7 + idx, np.ones_like(idx), np.zeros_like(idx))
+
+    raised = False
+    try:
+        rec = ensemble.solve_ensemble(8, 1, n_problems=n_problems, local_solver=fake)
+        if rank == 0:
+            np.save(out, rec)
+    except RuntimeError:
+        raised = True
+    assert raised == (rank == fail_rank)
+    dist.barrier()  # nobody is stuck in the gather
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_problems,fail_rank", [(1, -1), (5, 1)])
+def test_solve_ensemble_empty_shard_and_failing_rank(tmp_path, n_problems, fail_rank):
+    """More ranks than problems (rank 1 owns nothing) and a rank whose local solve raises: every rank still reaches the
+    single collective (the other ranks used to hang in all_gather)."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "rec.npy")
+    mp.spawn(_worker_solve, args=(2, _free_port(), n_problems, out, fail_rank), nprocs=2, join=True)
+    rec = np.load(out)
+    assert rec.shape == (n_problems, 5)
+    if fail_rank < 0:
+        np.testing.assert_array_equal(rec[:, 2], [7.0])
+    else:
+        np.testing.assert_array_equal(rec[:3, 2], [7.0, 8.0, 9.0])  # rank 0's shard
+        assert np.all(rec[3:, 4] == -1.0)                              # rank 1 reported its failure

@@ -481,6 +481,31 @@ def test_n_eigenpairs_partial_vs_oracle(G):
     assert np.linalg.norm(part["D"][0] - ref.density(o, o)[0]) < TOL_D
 
 
+def test_capi_ensemble_gather_single_rank(G):
+    """gscf_b200_comm_* / gscf_b200_ensemble_gather (include/gscf_b200.h section 3b) with a one-rank NCCL communicator:
+    the gathered records are the engine's own per-problem results, in problem order."""
+    from gscf_b200 import ensemble
+    from gscf_b200 import lib as L
+
+    assert L.lib.gscf_b200_nccl_version() > 0
+    n, o, aux, P = 32, 4, 4, 6
+    fock = G.DeviceDFFock(n, o, n_aux=aux, seeds=list(range(200, 200 + P)))
+    eng, st = G.solve_device_problem(fock, "diis", {"diis_n_prev_steps": 4, "max_iter": 60})
+    comm = ensemble.NcclGather()
+    try:
+        rec = comm.gather(eng, P)
+        e1, e2 = eng.energies()
+        np.testing.assert_array_equal(rec[:, 0], e1 + e2)
+        np.testing.assert_array_equal(rec[:, 2], eng.n_iter())
+        np.testing.assert_array_equal(rec[:, 3], eng.converged())
+        np.testing.assert_array_equal(rec[:, 4], eng.status())
+        np.testing.assert_array_equal(rec[:, 1], eng.error_norm())
+    finally:
+        comm.close()
+        eng.close()
+        fock.close()
+
+
 def test_c3_full_size_properties(G):
     """BASELINE configs[2] at full size (n_bf = 4096, n_occ = 512; n_aux = 64 as in bench.py) through the blocked
     tridiagonalisation: too large for the oracle inside a test, so the size-independent properties of a converged
