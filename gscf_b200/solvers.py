@@ -376,6 +376,18 @@ class Engine:
                                                       C.byref(k)))
         return out[:, : k.value]
 
+    def current_diis_coefficients(self, problem=0):
+        """Coefficients of the extrapolation being diagonalised right now (valid inside the NEW_DIAGMAT /
+        UPDATE_EIGENPAIRS hooks): [] before the first error, [1] with one, the device solution otherwise."""
+        k = int(L.lib.gscf_b200_get_history_size(self.handle))
+        if k <= 0:
+            return np.zeros(0)
+        if k == 1:
+            return np.ones(1)
+        out = np.zeros((self.P, k))
+        L.check(L.lib.gscf_b200_get_current_diis_coefficients(self.handle, out.ctypes.data_as(C.POINTER(C.c_double)), k))
+        return out[problem]
+
     def error_overlaps(self, problem=0):
         res = []
         i = 0
@@ -589,8 +601,12 @@ class ScfBase:
                         state._engine = eng
                         if ev in (L.EV_UPDATE_PROBLEM_MATRIX, L.EV_AFTER_ITERATION):
                             self._mirror_scalars(eng, state)
-                        if self._method == "diis" and ev in (L.EV_NEW_DIAGMAT, L.EV_AFTER_ITERATION):
-                            c = eng.diis_coefficients()  # public state member, PulayDiisScf.hh:83-86
+                        if self._method == "diis" and ev == L.EV_NEW_DIAGMAT:
+                            # public state member (PulayDiisScf.hh:83-86): the coefficients of THIS iteration's
+                            # extrapolation live on the device until the iteration's scalars are fetched
+                            state.diis_coefficients = eng.current_diis_coefficients()
+                        elif self._method == "diis" and ev == L.EV_AFTER_ITERATION:
+                            c = eng.diis_coefficients()  # the row recorded for the iteration that just ended
                             state.diis_coefficients = c[0] if c.size else np.zeros(0)
                         getattr(self, hooks[ev])(state)
                         return 0

@@ -7,8 +7,12 @@
 // What is identical to the reference: class / template names, public data members of the state
 // structs, virtual hooks, GenMap keys and defaults, iteration order, exceptions.  What differs:
 // the protected "building block" members (update_eigenpairs, ...) are not individually callable -
-// the loop lives behind gscf_b200_solve_{plain,diis,toda}; block-diagonal (alpha/beta) operators
-// are driven through the C ABI / Python layer only in this round.
+// the loop lives behind gscf_b200_solve_{plain,diis,toda}.  Unrestricted problems are block-diagonal
+// (alpha / beta) problem matrices (lazyten::BlockDiagonalMatrix<Block, 2>, ScfBase.hh:300-312,
+// OperatorLinearCombination.hh:49-84): the eigensolution then holds 2 n vectors of 2 n elements, alpha first.
+// Hook / mirror trampolines are registered only when the solver type overrides a hook; otherwise the
+// state members (rings, coefficients, eigensolutions) are materialised once, after the loop.
+// B200 extension: ScfBase::solve_ensemble runs P independent problems in one engine (lock step).
 #pragma once
 #include <cstring>
 #include <exception>
@@ -20,6 +24,14 @@
 #include "../gscf_b200.h"
 #include "../krims/krims.hh"
 #include "../lazyten/lazyten.hh"
+
+// GCC's bound-member-function extension: the address a virtual call on *this would reach, against the address of the
+// named class's own implementation.  Used to find out whether a hook is overridden (ScfBase::b200_hooks_overridden).
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC diagnostic ignored "-Wpmf-conversions"
+#define GSCF_B200_OVERRIDDEN_(Class, fn) \
+  ((b200_hook_fp)(this->*(&Class::fn)) != (b200_hook_fp)(&Class::fn))
+#endif
 
 namespace gscf {
 
@@ -145,19 +157,18 @@ class ScfStateBase : public lazyten::IterativeStateWrapper<lazyten::SolverStateB
   size_t n_mtx_applies() const override { return m_n_mtx_applies; }
   size_t& n_mtx_applies() { return m_n_mtx_applies; }
 
-  real_type last_error_norm;
+  // not yet evaluated: compares false against any threshold (ScfStateBase.hh:171)
+  real_type last_error_norm = lazyten::Constants<real_type>::invalid;
 
+  /** The state takes the problem matrix over (it is updated in place or copied on write later) and only subscribes
+   *  to the overlap, which has to outlive it (ScfStateBase.hh:168-184). */
   ScfStateBase(probmat_type prob_mat, const OverlapMatrix& overlap_mat)
-        : lazyten::IterativeStateWrapper<lazyten::SolverStateBase>{lazyten::SolverStateBase()},
-          last_error_norm{lazyten::Constants<real_type>::invalid},
-          problem_matrix_ptr{std::make_shared<probmat_type>(std::move(prob_mat))},
-          diagonalised_matrix_ptr{nullptr},
-          m_n_mtx_applies(0),
-          m_overlap_matrix_ptr{krims::make_subscription(overlap_mat, "ScfState")},
-          m_eigensolution{},
-          m_prev_eigensolution{} {
-    assert_dbg(problem_matrix_ptr->is_hermitian(100 * lazyten::Constants<real_type>::default_tolerance),
-               krims::ExcInvalidState("problem matrix not Hermitian"));
+        : problem_matrix_ptr(new probmat_type(std::move(prob_mat))),
+          m_overlap_matrix_ptr(krims::make_subscription(overlap_mat, "ScfState")) {
+#ifndef NDEBUG
+    const real_type herm_tol = 100 * lazyten::Constants<real_type>::default_tolerance;
+    if (!problem_matrix_ptr->is_hermitian(herm_tol)) throw krims::ExcInvalidState("problem matrix not Hermitian");
+#endif
   }
 
   template <typename DiagMat>
@@ -175,11 +186,11 @@ class ScfStateBase : public lazyten::IterativeStateWrapper<lazyten::SolverStateB
   }
 
   std::shared_ptr<probmat_type> problem_matrix_ptr;
-  std::shared_ptr<diagmat_type> diagonalised_matrix_ptr;
+  std::shared_ptr<diagmat_type> diagonalised_matrix_ptr;  // nullptr outside an iteration
 
  private:
   EigenproblemStatistics m_eprob_stats;
-  size_t m_n_mtx_applies;
+  size_t m_n_mtx_applies = 0;
   krims::SubscriptionPointer<const overlap_type> m_overlap_matrix_ptr;
   esoln_type m_eigensolution;
   esoln_type m_prev_eigensolution;
@@ -192,29 +203,58 @@ struct IsScfState<T, krims::VoidType<typename T::probmat_type, typename T::overl
       : public std::is_base_of<ScfStateBase<typename T::probmat_type, typename T::overlap_type, typename T::diagmat_type>,
                                T> {};
 
-// ---- OperatorLinearCombination (OperatorLinearCombination.hh:26-47) ----------------------------------------
+// ---- OperatorLinearCombination (OperatorLinearCombination.hh:26-84) ----------------------------------------
+// sum_i c_i F_i as a lazy sum; what the device materialises with axpby_n.  Primary template: ordinary operators.
 template <typename Operator, bool BlockDiagonal = lazyten::IsBlockDiagonalMatrix<Operator>::value>
-struct OperatorLinearCombination {
+struct OperatorLinearCombination : public lazyten::LazyMatrixSum<typename Operator::stored_matrix_type> {
   typedef Operator operator_type;
+  typedef lazyten::LazyMatrixSum<typename Operator::stored_matrix_type> base_type;
   typedef typename operator_type::scalar_type scalar_type;
   typedef typename operator_type::real_type real_type;
   typedef typename operator_type::size_type size_type;
   typedef typename operator_type::stored_matrix_type stored_matrix_type;
-  explicit OperatorLinearCombination(const operator_type& op, scalar_type coeff = 1) { push_term(op, coeff); }
-  void push_term(const operator_type& op, scalar_type coeff = 1) { m_terms.emplace_back(&op, coeff); }
-  size_t n_terms() const { return m_terms.size(); }
-  size_t n_rows() const { return m_terms.front().first->n_rows(); }
-  size_t n_cols() const { return m_terms.front().first->n_cols(); }
-  // lazily evaluated element of sum_i c_i F_i (the values the device kernel materialises)
-  scalar_type operator()(size_t i, size_t j) const {
-    scalar_type s = 0;
-    for (const auto& t : m_terms) s += t.second * (*t.first)(i, j);
-    return s;
-  }
-
- private:
-  std::vector<std::pair<const operator_type*, scalar_type>> m_terms;
+  explicit OperatorLinearCombination(const operator_type& op, scalar_type coeff = 1) : base_type(op, coeff) {}
+  void push_term(const operator_type& op, scalar_type coeff = 1) { this->add_term(op, coeff); }
 };
+
+// Block-diagonal operators with exactly two (alpha, beta) blocks: one lazy sum per block, every term contributes its
+// blocks with the SAME coefficient (OperatorLinearCombination.hh:49-84) - one DIIS / damping coefficient set for both spins.
+template <typename Operator>
+struct OperatorLinearCombination<Operator, true>
+      : public lazyten::BlockDiagonalMatrix<lazyten::LazyMatrixSum<typename Operator::stored_matrix_type>,
+                                            Operator::n_blocks> {
+  static_assert(Operator::n_blocks == 2, "OperatorLinearCombination of block-diagonal operators assumes two blocks");
+  typedef Operator operator_type;
+  typedef lazyten::LazyMatrixSum<typename Operator::stored_matrix_type> block_type;
+  typedef lazyten::BlockDiagonalMatrix<block_type, Operator::n_blocks> base_type;
+  typedef typename operator_type::scalar_type scalar_type;
+  typedef typename operator_type::real_type real_type;
+  typedef typename operator_type::size_type size_type;
+  typedef typename operator_type::stored_matrix_type stored_matrix_type;
+  explicit OperatorLinearCombination(const operator_type& op, scalar_type coeff = 1)
+        : base_type(std::array<block_type, 2>{block_type(op.diag_blocks()[0], coeff),
+                                              block_type(op.diag_blocks()[1], coeff)}) {}
+  void push_term(const operator_type& op, scalar_type coeff = 1) {
+    for (size_t b = 0; b < Operator::n_blocks; ++b) this->diag_blocks()[b].add_term(op.diag_blocks()[b], coeff);
+  }
+  size_t n_terms() const { return this->diag_blocks()[0].n_terms(); }
+};
+
+namespace b200 {
+// uniform block access to ordinary (one block) and block-diagonal (alpha / beta) problem matrices
+template <typename PM, bool BD = lazyten::IsBlockDiagonalMatrix<PM>::value>
+struct Blocks {
+  static constexpr size_t count = 1;
+  static size_t order(const PM& m) { return m.n_rows(); }
+  static double at(const PM& m, size_t, size_t i, size_t j) { return m(i, j); }
+};
+template <typename PM>
+struct Blocks<PM, true> {
+  static constexpr size_t count = PM::n_blocks;
+  static size_t order(const PM& m) { return m.diag_blocks()[0].n_rows(); }
+  static double at(const PM& m, size_t b, size_t i, size_t j) { return m.diag_blocks()[b](i, j); }
+};
+}  // namespace b200
 
 // ---- ScfBase (ScfBase.hh:48-370) ------------------------------------------------------------------------------
 template <typename State>
@@ -280,23 +320,49 @@ class ScfBase : public lazyten::IterativeWrapper<lazyten::SolverBase<State>> {
     return state;
   }
 
+  /** B200 extension (no counterpart in the reference): P independent problems of the same shape in ONE engine, driven
+   *  in lock step (a member leaves the active set when it converges or fails).  overlaps: one per problem or a single
+   *  shared one.  No hooks are dispatched; a failed member gets its fail flag set (state.is_failed()) instead of an
+   *  exception, so one bad problem does not abort the ensemble. */
+  std::vector<state_type> solve_ensemble(std::vector<probmat_type> probmats,
+                                         const std::vector<const overlap_type*>& overlaps) const {
+    assert_throw(!probmats.empty() && (overlaps.size() == 1 || overlaps.size() == probmats.size()),
+                 krims::ExcInvalidState("solve_ensemble: need one overlap per problem or a single shared one"));
+    std::vector<state_type> states;
+    states.reserve(probmats.size());
+    for (size_t p = 0; p < probmats.size(); ++p)
+      states.emplace_back(std::move(probmats[p]), *overlaps[overlaps.size() == 1 ? 0 : p]);
+    std::vector<state_type*> ptrs;
+    for (auto& st : states) ptrs.push_back(&st);
+    run_engine(ptrs, /*ensemble=*/true);
+    return states;
+  }
+
  protected:
   virtual void on_update_eigenpairs(state_type&) const {}
   virtual void on_update_problem_matrix(state_type&) const {}
   /** DIIS / TODA override this (PulayDiisScf.hh:202, TruncatedOptDampScf.hh:200). */
   virtual void on_new_diagmat_dispatch(state_type&) const {}
 
-  /** Residual error C_cur - C_prev (ScfBase.hh:268-289); every real user overrides it.  Solvers
-   *  wrapped in b200::DevicePulayError use the built-in device kernel instead. */
+  /** Default error (ScfBase.hh:268-289): how far the eigenvectors moved since the previous iteration, column by
+   *  column - sign dependent, every real user overrides it.  Before a second eigensolution exists the error is a
+   *  1 x 1 "invalid" matrix, i.e. not converged.  Solvers wrapped in b200::DevicePulayError use the device kernel. */
   virtual matrix_type calculate_error(const state_type& s) const {
-    if (s.previous_eigensolution().evectors().n_vectors() == 0)
-      return matrix_type{{lazyten::Constants<scalar_type>::invalid}};
-    const auto& prev_evec = s.previous_eigensolution().evectors();
-    const auto& cur_evec = s.eigensolution().evectors();
-    matrix_type ret(prev_evec.n_elem(), prev_evec.n_vectors(), false);
-    for (size_type j = 0; j < cur_evec.n_vectors(); ++j)
-      for (size_type i = 0; i < cur_evec.n_elem(); ++i) ret(i, j) = cur_evec[j](i) - prev_evec[j](i);
-    return ret;
+    const auto& before = s.previous_eigensolution().evectors();
+    const auto& now = s.eigensolution().evectors();
+    if (before.n_vectors() == 0) {
+      matrix_type not_yet(1, 1, false);
+      not_yet(0, 0) = lazyten::Constants<scalar_type>::invalid;
+      return not_yet;
+    }
+    const size_type n_vec = std::min(now.n_vectors(), before.n_vectors());
+    matrix_type diff(now.n_elem(), n_vec, false);
+    for (size_type v = 0; v < n_vec; ++v) {
+      const auto& cn = now[v];
+      const auto& cb = before[v];
+      for (size_type r = 0; r < now.n_elem(); ++r) diff(r, v) = cn(r) - cb(r);
+    }
+    return diff;
   }
   virtual bool b200_device_error() const { return false; }
 
@@ -305,55 +371,81 @@ class ScfBase : public lazyten::IterativeWrapper<lazyten::SolverBase<State>> {
   // ---- engine driver shared by the three algorithms ---------------------------------------------------
   enum class Method { Plain, Diis, Toda };
   struct Driver;
+  virtual Method b200_method() const = 0;
   virtual int b200_history() const { return 2; }
   virtual void b200_fill_params(gscf_b200_params&) const {}
   virtual void b200_after_fock(state_type&) const {}
+  /** per-iteration mirroring of algorithm state (only when a hook is overridden) */
   virtual void b200_mirror_iteration(state_type&, gscf_b200_engine*, int /*event*/) const {}
-  void run_engine(state_type& state, Method method) const;
+  /** one-off materialisation of algorithm state after the loop (problem p of the engine) */
+  virtual void b200_mirror_final(state_type&, gscf_b200_engine*, int /*p*/, int /*P*/) const {}
+  /** Does the dynamic type override any hook?  Decides whether the hook / mirror trampolines are registered at all
+   *  (hooks force a device -> host materialisation only if they exist). */
+  virtual bool b200_hooks_overridden() const {
+#if defined(__GNUC__) && !defined(__clang__)
+    return GSCF_B200_OVERRIDDEN_(ScfBase, before_iteration_step) ||
+           GSCF_B200_OVERRIDDEN_(ScfBase, after_iteration_step) ||
+           GSCF_B200_OVERRIDDEN_(ScfBase, on_update_eigenpairs) ||
+           GSCF_B200_OVERRIDDEN_(ScfBase, on_update_problem_matrix);
+#else
+    return true;  // no portable way to ask: always register
+#endif
+  }
+  void run_engine(std::vector<state_type*>& states, bool ensemble) const;
+  void run_engine(state_type& state) const {
+    std::vector<state_type*> one{&state};
+    run_engine(one, false);
+  }
+  typedef void (*b200_hook_fp)(const void*, state_type&);
 };
 
 template <typename State>
 struct ScfBase<State>::Driver {
+  typedef b200::Blocks<probmat_type> blocks;
   const ScfBase<State>* solver;
-  state_type* state;
+  std::vector<state_type*> states;
   gscf_b200_engine* eng = nullptr;
-  size_t n = 0;
-  int n_occ = 0;
-  int mirrored_iter = -1;
+  size_t n = 0;     // order of one block
+  size_t nblk = 1;  // 1 restricted, 2 alpha / beta
+  std::vector<int> mirrored_iter;
   std::exception_ptr error = nullptr;
-  Method method = Method::Plain;
 
   static void check(int st) {
     if (st != GSCF_B200_OK) throw b200::Error(st, gscf_b200_last_error());
   }
-  void mirror_eigensolution(const double* C, const double* w, int it) {
-    if (mirrored_iter == it) return;
+  // C: [nblk] n x n column-major, w: [nblk][n]  ->  the state's eigensolution.  Unrestricted: nblk * n vectors of
+  // nblk * n elements, alpha block first, zero outside the own block (how lazyten hands out block-diagonal eigenpairs,
+  // cf. the index ranges of TruncatedOptDampScf.hh:300-345).
+  void mirror_eigensolution(state_type& s, int p, const double* C, const double* w, int it) {
+    if (mirrored_iter[p] == it) return;
     typename state_type::esoln_type es;
-    // n_eigenpairs (ScfBase.hh:87): the eigensolution holds the k lowest pairs only
     const int kq = gscf_b200_get_n_eigenpairs(eng);
-    const size_t k = (kq > 0 && (size_t)kq < n) ? (size_t)kq : n;
-    es.evalues().assign(w, w + k);
-    auto mv = std::make_shared<lazyten::MultiVector<vector_type>>(n, k);
-    for (size_t j = 0; j < k; ++j)
-      for (size_t i = 0; i < n; ++i) (*mv)[j](i) = C[j * n + i];
+    const size_t k = (kq > 0 && (size_t)kq < n) ? (size_t)kq : n;  // n_eigenpairs (ScfBase.hh:87), per block
+    auto mv = std::make_shared<lazyten::MultiVector<vector_type>>(n * nblk, k * nblk);
+    es.evalues().resize(k * nblk);
+    for (size_t b = 0; b < nblk; ++b)
+      for (size_t j = 0; j < k; ++j) {
+        es.evalues()[b * k + j] = w[b * n + j];
+        const double* col = C + (b * n + j) * n;
+        for (size_t i = 0; i < n; ++i) (*mv)[b * k + j](b * n + i) = col[i];
+      }
     es.evectors_ptr = mv;
-    state->push_new_eigensolution(std::move(es), {0, 0});
-    mirrored_iter = it;
-  }
-  void mirror_from_engine(int it) {
-    if (mirrored_iter == it) return;
-    std::vector<double> C(n * n), w(n);
-    check(gscf_b200_get_coeff(eng, C.data(), (int)n));
-    check(gscf_b200_get_orben(eng, w.data()));
-    mirror_eigensolution(C.data(), w.data(), it);
+    s.push_new_eigensolution(std::move(es), {0, 0});
+    mirrored_iter[p] = it;
   }
   // host Fock builder: ScfBase::update_problem_matrix (ScfBase.hh:341-370) incl. copy-on-write
-  static int fock_tramp(void* ctx, int, int nb, int, const double* C, const double* w, double* F, double* e1,
+  static int fock_tramp(void* ctx, int p, int nb, int nblocks, const double* C, const double* w, double* F, double* e1,
                         double* e2) {
     Driver* d = static_cast<Driver*>(ctx);
     try {
-      state_type& s = *d->state;
-      d->mirror_eigensolution(C, w, (int)s.n_iter());
+      state_type& s = *d->states[p];
+      if (d->states.size() > 1) {  // ensembles: no hook keeps the iteration count current
+        int it = 0;
+        std::vector<int> its(d->states.size());
+        if (gscf_b200_get_n_iter(d->eng, its.data()) == GSCF_B200_OK) it = its[p];
+        s.set_iteration_count((size_t)it);
+      }
+      d->mirror_eigensolution(s, p, C, w, (int)s.n_iter());
       if (s.problem_matrix_ptr.use_count() > 1)
         s.problem_matrix_ptr = std::make_shared<probmat_type>(*s.problem_matrix_ptr);
       const std::string key = s.problem_matrix().scf_update_key();
@@ -361,8 +453,9 @@ struct ScfBase<State>::Driver {
       s.problem_matrix().update({{key, cptr}});
       d->solver->b200_after_fock(s);
       const probmat_type& pm = s.problem_matrix();
-      for (int j = 0; j < nb; ++j)
-        for (int i = 0; i < nb; ++i) F[(size_t)j * nb + i] = pm(i, j);
+      for (int b = 0; b < nblocks; ++b)
+        for (int j = 0; j < nb; ++j)
+          for (int i = 0; i < nb; ++i) F[((size_t)b * nb + j) * nb + i] = blocks::at(pm, b, i, j);
       *e1 = pm.energy_1e_terms();
       *e2 = pm.energy_2e_terms();
       return 0;
@@ -371,33 +464,46 @@ struct ScfBase<State>::Driver {
       return 1;
     }
   }
-  static int error_tramp(void* ctx, int, int nb, int, const double*, const double* C, const double* w, double* E) {
+  // calculate_error override (ScfBase.hh:217) -> [nblk] n x n: the diagonal blocks of an (nblk n)^2 error, or the first
+  // columns of a tall one (default residual error); a 1 x 1 matrix (first iteration of the residual error) is passed
+  // on as its single value
+  static int error_tramp(void* ctx, int p, int nb, int nblocks, const double*, const double* C, const double* w,
+                         double* E) {
     Driver* d = static_cast<Driver*>(ctx);
     try {
-      state_type& s = *d->state;
-      d->mirror_eigensolution(C, w, (int)s.n_iter());
+      state_type& s = *d->states[p];
+      d->mirror_eigensolution(s, p, C, w, (int)s.n_iter());
       const matrix_type e = d->solver->calculate_error(s);
-      if (e.n_rows() != (size_t)nb || e.n_cols() != (size_t)nb) {
-        // e.g. the residual error's 1x1 "invalid" matrix of the first iteration: propagate its value
-        for (size_t k = 0; k < (size_t)nb * nb; ++k) E[k] = 0.0;
+      const size_t N = (size_t)nb * nblocks;
+      for (size_t k = 0; k < (size_t)nblocks * nb * nb; ++k) E[k] = 0.0;
+      if (e.n_rows() != N) {
         E[0] = e.n_rows() ? e(0, 0) : lazyten::Constants<scalar_type>::invalid;
-        if (e.n_rows() == s.eigensolution().evectors().n_elem())
-          for (size_t j = 0; j < e.n_cols() && j < (size_t)nb; ++j)
-            for (size_t i = 0; i < e.n_rows(); ++i) E[j * nb + i] = e(i, j);
         return 0;
       }
-      for (int j = 0; j < nb; ++j)
-        for (int i = 0; i < nb; ++i) E[(size_t)j * nb + i] = e(i, j);
+      for (int b = 0; b < nblocks; ++b)
+        for (int j = 0; j < nb; ++j) {
+          const size_t col = (size_t)b * nb + j;
+          if (col >= e.n_cols()) continue;
+          for (int i = 0; i < nb; ++i) E[((size_t)b * nb + j) * nb + i] = e((size_t)b * nb + i, col);
+        }
       return 0;
     } catch (...) {
       d->error = std::current_exception();
       return 1;
     }
   }
-  static int hook_tramp(void* ctx, int ev, int it) {
+  void mirror_from_engine(state_type& s, int p, int it) {
+    if (mirrored_iter[p] == it) return;
+    const size_t P = states.size();
+    std::vector<double> C(P * nblk * n * n), w(P * nblk * n);
+    check(gscf_b200_get_coeff(eng, C.data(), (int)n));
+    check(gscf_b200_get_orben(eng, w.data()));
+    mirror_eigensolution(s, p, C.data() + (size_t)p * nblk * n * n, w.data() + (size_t)p * nblk * n, it);
+  }
+  static int hook_tramp(void* ctx, int ev, int it) {  // single problem only
     Driver* d = static_cast<Driver*>(ctx);
     try {
-      state_type& s = *d->state;
+      state_type& s = *d->states[0];
       s.set_iteration_count((size_t)it);
       switch (ev) {
         case GSCF_B200_EV_BEFORE_ITERATION:
@@ -408,7 +514,7 @@ struct ScfBase<State>::Driver {
           d->solver->on_new_diagmat_dispatch(s);
           break;
         case GSCF_B200_EV_UPDATE_EIGENPAIRS:
-          d->mirror_from_engine(it);
+          d->mirror_from_engine(s, 0, it);
           d->solver->b200_mirror_iteration(s, d->eng, ev);
           d->solver->on_update_eigenpairs(s);
           s.diagonalised_matrix_ptr.reset();
@@ -434,44 +540,68 @@ struct ScfBase<State>::Driver {
 };
 
 template <typename State>
-void ScfBase<State>::run_engine(state_type& state, Method method) const {
-  assert_throw(!state.is_failed(), krims::ExcInvalidState("Cannot solve a failed state"));
-  const probmat_type& pm0 = state.problem_matrix();
-  const size_t n = pm0.n_rows();
+void ScfBase<State>::run_engine(std::vector<state_type*>& states, bool ensemble) const {
+  typedef b200::Blocks<probmat_type> blocks;
+  const size_t P = states.size();
+  for (state_type* sp : states) assert_throw(!sp->is_failed(), krims::ExcInvalidState("Cannot solve a failed state"));
+  const probmat_type& pm0 = states[0]->problem_matrix();
+  const size_t nblk = blocks::count;
+  const size_t n = blocks::order(pm0);
   const krims::Range<size_t> occ_a = pm0.indices_orbspace(OrbitalSpace::OCC_ALPHA);
   const krims::Range<size_t> occ_b = pm0.indices_orbspace(OrbitalSpace::OCC_BETA);
-  assert_implemented(occ_a == occ_b);  // restricted problems through the C++ layer (see header note)
+  // restricted: one block, identical ranges.  Unrestricted (ScfBase.hh:300-312): a two-block problem matrix; the
+  // beta range indexes the second half of the eigensolution.  Anything else has no representation in the engine.
+  assert_implemented(nblk == 2 || occ_a == occ_b);
+  assert_implemented(nblk == 1 || n_eigenpairs == lazyten::Constants<size_type>::all || n_eigenpairs >= n * nblk);
 
-  Driver drv{this, &state};
+  Driver drv{this, states};
   drv.n = n;
-  drv.method = method;
+  drv.nblk = nblk;
+  drv.mirrored_iter.assign(P, -1);
   gscf_b200_config cfg{};
-  cfg.n_bas = (int)n; cfg.n_problems = 1; cfg.n_blocks = 1;
+  cfg.n_bas = (int)n; cfg.n_problems = (int)P; cfg.n_blocks = (int)nblk;
   cfg.n_alpha = (int)occ_a.length(); cfg.n_beta = (int)occ_b.length();
   cfg.max_history = std::max(2, b200_history());
-  cfg.eig_method = b200_eig_method; cfg.shared_overlap = 0; cfg.stream = nullptr;
+  cfg.eig_method = b200_eig_method; cfg.stream = nullptr;
+  bool shared = true;
+  for (size_t p = 1; p < P; ++p) shared = shared && (&states[p]->overlap_matrix() == &states[0]->overlap_matrix());
+  cfg.shared_overlap = (P > 1 && shared) ? 1 : 0;
   Driver::check(gscf_b200_engine_create(&cfg, &drv.eng));
   struct Guard {
     gscf_b200_engine* e;
     ~Guard() { gscf_b200_engine_destroy(e); }
   } guard{drv.eng};
 
-  std::vector<double> buf(n * n);
-  const overlap_type& S = state.overlap_matrix();
-  for (size_t j = 0; j < n; ++j)
-    for (size_t i = 0; i < n; ++i) buf[j * n + i] = S(i, j);
-  Driver::check(gscf_b200_set_overlap(drv.eng, buf.data(), (int)n, GSCF_B200_HOST));
+  {  // overlap: the (first) n x n diagonal block of every state's overlap
+    const size_t nS = cfg.shared_overlap ? 1 : P;
+    std::vector<double> buf(nS * n * n);
+    for (size_t p = 0; p < nS; ++p) {
+      const overlap_type& S = states[p]->overlap_matrix();
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) buf[(p * n + j) * n + i] = S(i, j);
+    }
+    Driver::check(gscf_b200_set_overlap(drv.eng, buf.data(), (int)n, GSCF_B200_HOST));
+  }
 
   auto* dev = dynamic_cast<const b200::DeviceFockBuilder_i*>(&pm0);
   if (dev) Driver::check(gscf_b200_set_fock_builder_device(drv.eng, dev->device_fock_fn(), dev->device_fock_ctx()));
   else Driver::check(gscf_b200_set_fock_builder_host(drv.eng, &Driver::fock_tramp, &drv));
   if (!b200_device_error()) Driver::check(gscf_b200_set_error_host(drv.eng, &Driver::error_tramp, &drv));
-  Driver::check(gscf_b200_set_hook(drv.eng, &Driver::hook_tramp, &drv));
+  const bool hooks = !ensemble && b200_hooks_overridden();
+  if (hooks) Driver::check(gscf_b200_set_hook(drv.eng, &Driver::hook_tramp, &drv));
 
-  for (size_t j = 0; j < n; ++j)
-    for (size_t i = 0; i < n; ++i) buf[j * n + i] = pm0(i, j);
-  const double e1 = pm0.energy_1e_terms(), e2 = pm0.energy_2e_terms();
-  Driver::check(gscf_b200_set_problem_matrix(drv.eng, buf.data(), (int)n, GSCF_B200_HOST, &e1, &e2));
+  {  // the problem matrices handed to solve() with their energies
+    std::vector<double> buf(P * nblk * n * n), e1(P), e2(P);
+    for (size_t p = 0; p < P; ++p) {
+      const probmat_type& pm = states[p]->problem_matrix();
+      for (size_t b = 0; b < nblk; ++b)
+        for (size_t j = 0; j < n; ++j)
+          for (size_t i = 0; i < n; ++i) buf[((p * nblk + b) * n + j) * n + i] = blocks::at(pm, b, i, j);
+      e1[p] = pm.energy_1e_terms();
+      e2[p] = pm.energy_2e_terms();
+    }
+    Driver::check(gscf_b200_set_problem_matrix(drv.eng, buf.data(), (int)n, GSCF_B200_HOST, e1.data(), e2.data()));
+  }
 
   gscf_b200_params prm;
   gscf_b200_default_params(&prm);
@@ -480,32 +610,57 @@ void ScfBase<State>::run_engine(state_type& state, Method method) const {
   prm.n_eigenpairs = (n_eigenpairs == lazyten::Constants<size_type>::all || n_eigenpairs >= n) ? -1 : (long long)n_eigenpairs;
   b200_fill_params(prm);
   int st = GSCF_B200_OK;
-  switch (method) {
+  switch (b200_method()) {
     case Method::Plain: st = gscf_b200_solve_plain(drv.eng, &prm); break;
     case Method::Diis: st = gscf_b200_solve_diis(drv.eng, &prm); break;
     case Method::Toda: st = gscf_b200_solve_toda(drv.eng, &prm); break;
   }
-  // mirror the final state
-  int nit = 0;
-  gscf_b200_get_n_iter(drv.eng, &nit);
-  state.set_iteration_count((size_t)nit);
-  double err = 0;
-  gscf_b200_get_error_norm(drv.eng, &err);
-  state.last_error_norm = err;
-  long long napp = 0;
-  gscf_b200_get_n_mtx_applies(drv.eng, &napp);
-  state.n_mtx_applies() = (size_t)napp;
+  // materialise the final state(s)
+  std::vector<int> nit(P, 0), status(P, 0);
+  std::vector<double> err(P, 0.0), ea(P, 0.0), eb(P, 0.0);
+  std::vector<long long> napp(P, 0);
+  gscf_b200_get_n_iter(drv.eng, nit.data());
+  gscf_b200_get_status(drv.eng, status.data());
+  gscf_b200_get_error_norm(drv.eng, err.data());
+  gscf_b200_get_n_mtx_applies(drv.eng, napp.data());
+  for (size_t p = 0; p < P; ++p) {
+    states[p]->set_iteration_count((size_t)nit[p]);
+    states[p]->last_error_norm = err[p];
+    states[p]->n_mtx_applies() = (size_t)napp[p];
+  }
   if (dev) {
-    double a = 0, b = 0;
-    gscf_b200_get_energies(drv.eng, &a, &b);
-    const_cast<b200::DeviceFockBuilder_i*>(dev)->set_energies(a, b);
+    gscf_b200_get_energies(drv.eng, ea.data(), eb.data());
+    const_cast<b200::DeviceFockBuilder_i*>(dev)->set_energies(ea[0], eb[0]);
   }
   if (st == GSCF_B200_ERR_CALLBACK && drv.error) {
-    state.fail("callback threw");
+    for (state_type* sp : states) sp->fail("callback threw");
     std::rethrow_exception(drv.error);
   }
-  if (nit > 0 && st != GSCF_B200_ERR_CALLBACK) drv.mirror_from_engine(nit);
-  state.diagonalised_matrix_ptr.reset();
+  if (st != GSCF_B200_ERR_CALLBACK) {
+    std::vector<double> C, w;
+    for (size_t p = 0; p < P; ++p) {
+      if (nit[p] <= 0 || drv.mirrored_iter[p] == nit[p]) continue;
+      if (C.empty()) {  // one device -> host copy for the whole ensemble
+        C.resize(P * nblk * n * n);
+        w.resize(P * nblk * n);
+        Driver::check(gscf_b200_get_coeff(drv.eng, C.data(), (int)n));
+        Driver::check(gscf_b200_get_orben(drv.eng, w.data()));
+      }
+      drv.mirror_eigensolution(*states[p], (int)p, C.data() + p * nblk * n * n, w.data() + p * nblk * n, nit[p]);
+    }
+    if (!hooks)
+      for (size_t p = 0; p < P; ++p) b200_mirror_final(*states[p], drv.eng, (int)p, (int)P);
+  }
+  for (state_type* sp : states) sp->diagonalised_matrix_ptr.reset();
+  auto message = [&](int code) -> std::string { return std::string(gscf_b200_last_error()) + " (status " + std::to_string(code) + ")"; };
+  if (ensemble) {
+    for (size_t p = 0; p < P; ++p)
+      if (status[p] != GSCF_B200_OK) states[p]->fail(message(status[p]));
+    if (st != GSCF_B200_OK && st != GSCF_B200_ERR_MAX_ITER && st != GSCF_B200_ERR_DIIS_STEP && st != GSCF_B200_ERR_EIGENSOLVER)
+      throw b200::Error(st, gscf_b200_last_error());
+    return;
+  }
+  state_type& state = *states[0];
   switch (st) {
     case GSCF_B200_OK: return;
     case GSCF_B200_ERR_MAX_ITER:
@@ -549,9 +704,10 @@ class PlainScf : public ScfBase<ScfState> {
   PlainScf(const krims::GenMap& map) : PlainScf() { update_control_params(map); }
   void update_control_params(const krims::GenMap& map) { base_type::update_control_params(map); }
   void get_control_params(krims::GenMap& map) const { base_type::get_control_params(map); }
-  void solve_state(state_type& state) const override { this->run_engine(state, base_type::Method::Plain); }
+  void solve_state(state_type& state) const override { this->run_engine(state); }
 
  protected:
+  typename base_type::Method b200_method() const override { return base_type::Method::Plain; }
   void b200_mirror_iteration(state_type& s, gscf_b200_engine*, int ev) const override {
     if (ev == GSCF_B200_EV_UPDATE_EIGENPAIRS) s.diagonalised_matrix_ptr = s.problem_matrix_ptr;  // PlainScf.hh:129
   }
@@ -619,39 +775,66 @@ class PulayDiisScf : public ScfBase<ScfState> {
   }
   void solve_state(state_type& state) const override {
     state.resize_buffers(n_prev_steps);  // PulayDiisScf.hh:289
-    this->run_engine(state, base_type::Method::Diis);
+    this->run_engine(state);
+  }
+  /** B200 extension, see ScfBase::solve_ensemble. */
+  std::vector<state_type> solve_ensemble(std::vector<probmat_type> probmats,
+                                         const std::vector<const overlap_type*>& overlaps) const {
+    std::vector<state_type> res = base_type::solve_ensemble(std::move(probmats), overlaps);
+    return res;
   }
 
-  /** The bordered DIIS system of the current state (PulayDiisScf.hh:326-356). */
+  /** The bordered DIIS system of the current state (PulayDiisScf.hh:326-356): entry (row, col <= row) is the overlap of
+   *  error `row` with error `col`, stored newest-first in overlap vector `row` at position row - col; the border row
+   *  and column are -1, the corner stays 0. */
   matrix_type diis_linear_system_matrix(const state_type& s) const {
-    size_type n_errors = s.error_overlaps.size();
-    matrix_type B(n_errors + 1, n_errors + 1, false);
-    auto it = std::begin(s.error_overlaps);
-    for (size_type i = 0; i < n_errors; ++i, ++it) {
-      B(i, i) = (*it)[0];
-      for (size_type j = 1; j < i + 1; ++j) B(i, i - j) = B(i - j, i) = (*it)[j];
-      B(n_errors, i) = B(i, n_errors) = -1.;
+    std::vector<const std::vector<scalar_type>*> ov;
+    for (const auto& v : s.error_overlaps) ov.push_back(&v);
+    const size_type k = ov.size();
+    matrix_type B(k + 1, k + 1, true);
+    for (size_type row = 0; row < k; ++row) {
+      for (size_type col = 0; col <= row; ++col) {
+        const scalar_type v = (*ov[row])[row - col];
+        B(row, col) = v;
+        B(col, row) = v;
+      }
+      B(row, k) = -1.;
+      B(k, row) = -1.;
     }
-    B(n_errors, n_errors) = 0.;
     return B;
   }
 
  protected:
   virtual void on_new_diagmat(state_type&) const {}
   void on_new_diagmat_dispatch(state_type& s) const override { on_new_diagmat(s); }
+  typename base_type::Method b200_method() const override { return base_type::Method::Diis; }
+  bool b200_hooks_overridden() const override {
+#if defined(__GNUC__) && !defined(__clang__)
+    typedef typename base_type::b200_hook_fp b200_hook_fp;
+    return base_type::b200_hooks_overridden() || GSCF_B200_OVERRIDDEN_(PulayDiisScf, on_new_diagmat);
+#else
+    return true;
+#endif
+  }
   int b200_history() const override { return (int)n_prev_steps; }
   void b200_fill_params(gscf_b200_params& p) const override { p.diis_n_prev_steps = (int)n_prev_steps; }
   void b200_after_fock(state_type& s) const override {
+    if (s.prev_problem_matrix_ptrs.max_size() != n_prev_steps) s.resize_buffers(n_prev_steps);
     s.prev_problem_matrix_ptrs.push_back(s.problem_matrix_ptr);  // PulayDiisScf.hh:315
   }
+  // [nblk] n x n blocks from the engine -> the state's error matrix ((nblk n)^2, block diagonal)
+  static matrix_type b200_error_matrix(const double* E, size_t n, size_t nblk) {
+    matrix_type e(n * nblk, n * nblk, true);
+    for (size_t b = 0; b < nblk; ++b)
+      for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < n; ++i) e(b * n + i, b * n + j) = E[(b * n + j) * n + i];
+    return e;
+  }
   void b200_mirror_iteration(state_type& s, gscf_b200_engine* eng, int ev) const override {
+    typedef b200::Blocks<probmat_type> blocks;
     if (ev == GSCF_B200_EV_NEW_DIAGMAT) {
-      // diis_coefficients (oldest -> newest) and the lazy linear combination (:358-433)
-      std::vector<double> c(16, 0.0);
-      int k = 0;
-      gscf_b200_get_diis_coefficients(eng, c.data(), &k);
-      // the coefficients of *this* iteration live on the device; k == history size
-      k = (int)s.prev_problem_matrix_ptrs.size();
+      // diis_coefficients (oldest -> newest) of THIS iteration and the lazy linear combination (:358-433)
+      const int k = (int)s.prev_problem_matrix_ptrs.size();
       std::vector<double> coeff(k, 0.0);
       if (k == 1) coeff[0] = 1.0;
       if (k >= 2) gscf_b200_get_current_diis_coefficients(eng, coeff.data(), k);
@@ -667,16 +850,34 @@ class PulayDiisScf : public ScfBase<ScfState> {
       }
     } else if (ev == GSCF_B200_EV_AFTER_ITERATION) {
       // errors.push_back / append_new_overlaps (:318-320, :440-463)
-      const size_t n = s.problem_matrix().n_rows();
-      std::vector<double> E(n * n);
+      const size_t n = blocks::order(s.problem_matrix()), nblk = blocks::count;
+      std::vector<double> E(nblk * n * n);
       gscf_b200_get_error(eng, E.data(), (int)n);
-      matrix_type e(n, n, false);
-      std::memcpy(e.memptr(), E.data(), n * n * sizeof(double));
-      s.errors.push_back(std::move(e));
+      s.errors.push_back(b200_error_matrix(E.data(), n, nblk));
       const int k = (int)s.errors.size();
       std::vector<double> ov(16, 0.0);
       int len = 0;
       if (gscf_b200_get_error_overlaps(eng, 0, k - 1, ov.data(), &len) == GSCF_B200_OK)
+        s.error_overlaps.push_back(std::vector<scalar_type>(ov.begin(), ov.begin() + len));
+    }
+  }
+  // no hook overridden: the rings and the last coefficients are fetched once, after the loop
+  void b200_mirror_final(state_type& s, gscf_b200_engine* eng, int p, int P) const override {
+    typedef b200::Blocks<probmat_type> blocks;
+    const size_t n = blocks::order(s.problem_matrix()), nblk = blocks::count;
+    if (s.errors.max_size() != n_prev_steps) s.resize_buffers(n_prev_steps);
+    const int k = gscf_b200_get_history_size(eng);
+    std::vector<double> c((size_t)P * 16, 0.0);
+    int kc = 0;
+    if (gscf_b200_get_diis_coefficients(eng, c.data(), &kc) == GSCF_B200_OK && kc > 0)
+      s.diis_coefficients = vector_type(c.begin() + (size_t)p * 16, c.begin() + (size_t)p * 16 + kc);
+    std::vector<double> E((size_t)P * nblk * n * n);
+    for (int i = 0; i < k; ++i) {
+      if (gscf_b200_get_error_entry(eng, i, E.data(), (int)n) != GSCF_B200_OK) break;
+      s.errors.push_back(b200_error_matrix(E.data() + (size_t)p * nblk * n * n, n, nblk));
+      std::vector<double> ov(16, 0.0);
+      int len = 0;
+      if (gscf_b200_get_error_overlaps(eng, p, i, ov.data(), &len) == GSCF_B200_OK)
         s.error_overlaps.push_back(std::vector<scalar_type>(ov.begin(), ov.begin() + len));
     }
   }
@@ -736,12 +937,25 @@ class TruncatedOptDampScf : public ScfBase<ScfState> {
   }
   void solve_state(state_type& state) const override {
     assert_implemented(n_prev_steps == 2);  // TruncatedOptDampScf.hh:243
-    this->run_engine(state, base_type::Method::Toda);
+    this->run_engine(state);
   }
 
  protected:
   virtual void on_new_diagmat(state_type&) const {}
   void on_new_diagmat_dispatch(state_type& s) const override { on_new_diagmat(s); }
+  typename base_type::Method b200_method() const override { return base_type::Method::Toda; }
+  bool b200_hooks_overridden() const override {
+#if defined(__GNUC__) && !defined(__clang__)
+    typedef typename base_type::b200_hook_fp b200_hook_fp;
+    return base_type::b200_hooks_overridden() || GSCF_B200_OVERRIDDEN_(TruncatedOptDampScf, on_new_diagmat);
+#else
+    return true;
+#endif
+  }
+  void b200_mirror_final(state_type& s, gscf_b200_engine* eng, int p, int P) const override {
+    std::vector<double> damp((size_t)P, 1.0);
+    if (gscf_b200_get_damping_coeff(eng, damp.data()) == GSCF_B200_OK) s.damping_coeff = damp[p];
+  }
   void b200_fill_params(gscf_b200_params& p) const override {
     p.toda_n_prev_steps = (int)n_prev_steps;
     p.toda_min_fock_prefactor = min_fock_prefactor;

@@ -4,6 +4,7 @@
 // so that user plugins written against lazyten (e.g. gscfmock::FockMatrix, pulay_error) compile;
 // they are host reference loops, not the product path.
 #pragma once
+#include <array>
 #include <cmath>
 #include <initializer_list>
 #include <limits>
@@ -224,8 +225,55 @@ template <typename T>
 struct StoredTypeOf {
   typedef typename T::stored_matrix_type type;
 };
-template <typename T>
+// BlockDiagonalMatrix<Block, N> / IsBlockDiagonalMatrix / LazyMatrixSum: the surface OperatorLinearCombination.hh:26-84
+// and ScfBase.hh:300-312 touch.  An unrestricted (alpha / beta) problem matrix derives from BlockDiagonalMatrix<Block, 2>.
+template <typename Block, size_t N>
+class BlockDiagonalMatrix {
+ public:
+  typedef Block block_type;
+  typedef typename Block::stored_matrix_type stored_matrix_type;
+  typedef typename stored_matrix_type::scalar_type scalar_type;
+  typedef typename stored_matrix_type::real_type real_type;
+  typedef typename stored_matrix_type::size_type size_type;
+  typedef typename stored_matrix_type::vector_type vector_type;
+  static constexpr size_t n_blocks = N;
+  explicit BlockDiagonalMatrix(std::array<Block, N> blocks) : m_blocks(std::move(blocks)) {}
+  virtual ~BlockDiagonalMatrix() = default;
+  BlockDiagonalMatrix(const BlockDiagonalMatrix&) = default;
+  BlockDiagonalMatrix(BlockDiagonalMatrix&&) = default;
+  BlockDiagonalMatrix& operator=(const BlockDiagonalMatrix&) = default;
+  BlockDiagonalMatrix& operator=(BlockDiagonalMatrix&&) = default;
+  const std::array<Block, N>& diag_blocks() const { return m_blocks; }
+  std::array<Block, N>& diag_blocks() { return m_blocks; }
+  size_t n_rows() const {
+    size_t r = 0;
+    for (const auto& b : m_blocks) r += b.n_rows();
+    return r;
+  }
+  size_t n_cols() const { return n_rows(); }
+  scalar_type operator()(size_t row, size_t col) const {
+    size_t off = 0;
+    for (const auto& b : m_blocks) {
+      const size_t nb = b.n_rows();
+      if (row < off + nb) return (col >= off && col < off + nb) ? b(row - off, col - off) : scalar_type(0);
+      off += nb;
+    }
+    return scalar_type(0);
+  }
+  bool is_hermitian(real_type tol = Constants<real_type>::default_tolerance) const {
+    for (const auto& b : m_blocks)
+      if (!b.is_hermitian(tol)) return false;
+    return true;
+  }
+
+ private:
+  std::array<Block, N> m_blocks;
+};
+template <typename T, typename = void>
 struct IsBlockDiagonalMatrix : public std::false_type {};
+template <typename T>
+struct IsBlockDiagonalMatrix<T, krims::VoidType<typename T::block_type, decltype(T::n_blocks)>>
+      : public std::is_base_of<BlockDiagonalMatrix<typename T::block_type, T::n_blocks>, T> {};
 
 // Lazy matrix interface (what a problem matrix plugin derives from, FockMatrix.hh:91)
 template <typename StoredMatrix>
@@ -254,6 +302,37 @@ class LazyMatrix_i {
       }
     return true;
   }
+};
+
+// sum_i c_i M_i of lazy matrices, evaluated element-wise on demand (the terms must outlive the sum)
+template <typename StoredMatrix>
+class LazyMatrixSum {
+ public:
+  typedef StoredMatrix stored_matrix_type;
+  typedef typename StoredMatrix::scalar_type scalar_type;
+  typedef typename StoredMatrix::real_type real_type;
+  typedef typename StoredMatrix::size_type size_type;
+  typedef typename StoredMatrix::vector_type vector_type;
+  typedef LazyMatrix_i<StoredMatrix> term_type;
+  LazyMatrixSum() {}
+  LazyMatrixSum(const term_type& op, scalar_type coeff) { add_term(op, coeff); }
+  void add_term(const term_type& op, scalar_type coeff) { m_terms.emplace_back(&op, coeff); }
+  size_t n_terms() const { return m_terms.size(); }
+  size_t n_rows() const { return m_terms.empty() ? 0 : m_terms.front().first->n_rows(); }
+  size_t n_cols() const { return m_terms.empty() ? 0 : m_terms.front().first->n_cols(); }
+  scalar_type operator()(size_t i, size_t j) const {
+    scalar_type s = 0;
+    for (const auto& t : m_terms) s += t.second * (*t.first)(i, j);
+    return s;
+  }
+  bool is_hermitian(real_type tol = Constants<real_type>::default_tolerance) const {
+    for (const auto& t : m_terms)
+      if (!t.first->is_hermitian(tol)) return false;
+    return true;
+  }
+
+ private:
+  std::vector<std::pair<const term_type*, scalar_type>> m_terms;
 };
 
 // matrix x multivector

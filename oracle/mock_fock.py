@@ -35,7 +35,10 @@ class MockFockProblem:
     """
 
     def __init__(self, idata: IntegralsSturmian14, n_alpha: int, n_beta: int):
-        assert n_alpha == n_beta  # FockMatrix.cc:177
+        # The reference asserts closed shell (FockMatrix.cc:177).  n_alpha != n_beta is an extension used to test the
+        # unrestricted (block-diagonal) branch of the solvers (ScfBase.hh:300-312) - PARITY UNPINNED: the same J / K /
+        # energy formulas (they are written per spin in FockMatrix.cc:157-167), F^s = T + V0 + J(Pa + Pb) - K(P^s).
+        self.unrestricted = n_alpha != n_beta
         self.idata = idata
         self.n_bas = idata.nbas
         self.n_alpha, self.n_beta = n_alpha, n_beta
@@ -49,7 +52,7 @@ class MockFockProblem:
         if C.ndim == 2:
             C = C[None]
         ca = C[0][:, : self.n_alpha]
-        cb = C[0][:, : self.n_beta]
+        cb = C[1 if (self.unrestricted and C.shape[0] > 1) else 0][:, : self.n_beta]
         pa = ca @ ca.T  # FockMatrix.cc:202-203
         pb = cb @ cb.T
         pt = pa + pb
@@ -76,6 +79,8 @@ class MockFockProblem:
             energy_2e_terms=e2,
             energy_total=e1 + e2,
         )
+        if self.unrestricted:
+            return np.stack([F, idata.t_bb + idata.v0_bb + j - kb]), e1, e2
         return F[None].copy(), e1, e2
 
 

@@ -29,6 +29,21 @@ def test_cpp_layer_compiles_and_links():
     assert os.path.exists(_build())
 
 
+def test_cpp_host_layer_probe_cpu():
+    """CPU: hook-override detection (lazy trampolines), OperatorLinearCombination for ordinary and block-diagonal
+    operators, the DIIS system layout and the default residual error - tests/cpp/hooks_probe.cc, no engine created."""
+    from gscf_b200 import lib as L
+
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = os.path.join(HERE, "cpp", "hooks_probe.bin")
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "cpp", "hooks_probe.cc"),
+           "-o", exe, "-L" + libdir, "-lgscf_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "PROBE OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_reference_header_names_exist():
     for name in ["ScfBase", "ScfStateBase", "PlainScf", "PulayDiisScf", "TruncatedOptDampScf", "ScfProblemMatrix_i",
                  "FocklikeMatrix_i", "ScfBaseKeys", "PlainScfKeys", "PulayDiisScfKeys", "TruncatedOptDampScfKeys",
@@ -52,6 +67,16 @@ def test_cpp_functionality_on_gpu(tmp_path):
             f.write(" ".join(repr(x) for x in row) + "\n")
         f.write(" ".join(repr(g[k]) for k in ["exp_energy_1e_terms", "exp_energy_coulomb", "exp_energy_exchange",
                                                 "exp_energy_total"]) + "\n")
+        # the unrestricted mock (n_alpha = 2, n_beta = 1) through the oracle: iteration counts, energy, orbital energies
+        from oracle import plain_scf, pulay_diis_scf, truncated_opt_damp_scf
+        from oracle.mock_fock import IntegralsSturmian14, MockFockProblem, functionality_test_guess
+
+        prob = MockFockProblem(IntegralsSturmian14(4.0, 1.0), 2, 1)
+        g0 = functionality_test_guess()
+        F0, e1, e2 = prob.fock(np.stack([g0, g0]))
+        rp, rd, rt = (fn(prob, F0, e1, e2) for fn in (plain_scf, pulay_diis_scf, truncated_opt_damp_scf))
+        f.write(f"{rp.n_iter} {rd.n_iter} {rt.n_iter} {rd.energy_total!r}\n")
+        f.write(" ".join(repr(float(x)) for x in rd.orben.ravel()) + "\n")
     r = subprocess.run([exe, str(binf), str(txt)], capture_output=True, text=True, timeout=300)
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

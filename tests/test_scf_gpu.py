@@ -121,6 +121,26 @@ def test_hooks_and_custom_error(G):
     assert sum(1 for c in calls if c[0] == "before") == 6
 
 
+def test_diis_coefficients_inside_on_new_diagmat(G):
+    """state.diis_coefficients inside on_new_diagmat are the coefficients of THIS iteration's extrapolation
+    (PulayDiisScf.hh:83-86, :358-433): [] / [1] / the solution of the bordered system - against the oracle's trace."""
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+
+    seen = []
+
+    class Rec(G.PulayDiisScf):
+        def on_new_diagmat(self, s):
+            seen.append(np.array(s.diis_coefficients, dtype=float).copy())
+
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    res = Rec().solve(fock, fock.s_bb)
+    o = _oracle_mock(GOLD["k_exp"], functionality_guess(), "diis")
+    assert res.n_iter() == o.n_iter == len(seen)
+    for got, ref in zip(seen, o.trace_coeff):
+        assert len(got) == len(ref)
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-9)
+
+
 def test_max_iter_and_control_params(G):
     from helpers import GOLD, Sturmian14Fock, functionality_guess
 
