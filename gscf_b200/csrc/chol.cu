@@ -113,10 +113,11 @@ int cholesky_inverse_batched(int n, double* A, int lda, long long sA, double* Lw
   GSCF_CHECK_LAUNCH();
   const int nblk = ceil_div(n, CB);
   constexpr size_t kDiagSmem = 2 * (size_t)CB * CLD * sizeof(double);
-  static bool cfg = false;
-  if (!cfg) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(dev)) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDiagSmem));
-    cfg = true;
+    once.done(dev);
   }
   // ---- factorisation: L (strictly lower blocks) into Lw, L_ii^-1 into the diagonal blocks of X ---------------------
   for (int b = 0; b < nblk; ++b) {

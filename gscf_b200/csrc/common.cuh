@@ -1,6 +1,7 @@
 // gscf-b200: shared device/host helpers for the sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,22 @@ void count_launch(int n = 1);
 enum PhaseId { PH_TRIDIAG = 8, PH_STEDC = 9, PH_BACKTRANSFORM = 10, PH_SYMV_SAMPLE = 11, PH_ORTHO_GEMM = 12,
                PH_TRAILING_GEMM = 13 };
 void phase_mark(int id, bool begin, cudaStream_t st);
+
+// Kernel function attributes (opt-in shared memory, cluster sizes) are PER DEVICE: a `static bool configured` would leave
+// the second GPU a process drives unconfigured.  One bit per device ordinal; safe under concurrent host threads (a race
+// only repeats the idempotent cudaFuncSetAttribute).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0ull};
+  // true: the caller still has to configure the current device (returned in dev)
+  bool need(int& dev) {
+    dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 64 || !(mask.load(std::memory_order_acquire) >> dev & 1ull);
+  }
+  void done(int dev) {
+    if (dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 inline int ceil_div(int x, int m) { return (x + m - 1) / m; }

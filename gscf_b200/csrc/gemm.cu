@@ -284,10 +284,11 @@ static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cuda
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
   auto kern = dgemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(dev)) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    once.done(dev);
   }
   dim3 grid(ceil_div(max_m, BM), ceil_div(max_n, BN), batch);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return GSCF_B200_OK;

@@ -241,14 +241,15 @@ int jacobi_syev_batched(int n, const double* A, int lda, long long strideA, doub
   const int threads = warps * 32;
 #define GSCF_JACOBI_LAUNCH(NPL, PPW)                                                                \
   do {                                                                                           \
-    static bool cfg = false;                                                                     \
-    if (!cfg) {                                                                                  \
+    static PerDeviceOnce once;                                                                   \
+    int dev_;                                                                                    \
+    if (once.need(dev_)) {                                                                       \
       GSCF_CUDA_TRY(cudaFuncSetAttribute(jacobi_onesided_kernel<NPL, PPW>,                        \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                          (int)jacobi_smem_bytes(32 * NPL > kJacobiMaxN          \
                                                                     ? kJacobiMaxN               \
                                                                     : 32 * NPL)));              \
-      cfg = true;                                                                                \
+      once.done(dev_);                                                                           \
     }                                                                                            \
     jacobi_onesided_kernel<NPL, PPW><<<batch, threads, smem, st>>>(A, lda, strideA, w, stride_w, Z, \
                                                               ldz, strideZ, n, batch_map,       \

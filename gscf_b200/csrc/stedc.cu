@@ -614,11 +614,14 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
   dc_split_kernel<<<dim3(std::max(1, ceil_div(n, 256)), batch), 256, 0, st>>>(d, e, dstride, ws, map);
   count_launch(1);
   GSCF_CHECK_LAUNCH();
-  static bool leaf_cfg = false;
   const size_t leaf_smem = (size_t)kLeafWarps * (kLeaf * kLeaf + 2 * kLeaf) * sizeof(double);
-  if (!leaf_cfg) {
+  static PerDeviceOnce once;
+  int dev;
+  const bool configure = once.need(dev);
+  if (configure) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_leaf_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem));
-    leaf_cfg = true;
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    once.done(dev);
   }
   zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[cur], bufld[cur], bufs[cur], n, map);
   dc_leaf_tql2_kernel<<<(unsigned)ceil_div_ll((long long)ws.nleaf * batch, kLeafWarps), kLeafWarps * 32, leaf_smem, st>>>(
@@ -626,11 +629,6 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   int lev = 0;
-  static bool cfg = false;
-  if (!cfg) {
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    cfg = true;
-  }
   // ---- merges -----------------------------------------------------------------------------------------
   for (int h = 1; h <= L; ++h) {
     const int nodes = 1 << (L - h);

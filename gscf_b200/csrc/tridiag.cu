@@ -8,14 +8,15 @@
 // Tridiagonalisation - the production path is the fused one-launch reduction of trd_fused.cuh / trd_fused_blk.cuh
 // (tridiagonalise_fused below picks the variant: single CTA in registers or shared memory, cluster per matrix,
 // cooperative group with the columns in registers / shared memory / L2, blocked for matrices larger than L2).
-// The older panel schemes are kept as fall-backs (GSCF_B200_TRD_FUSED=0, exercised by the variant tests):
-//   legacy (GSCF_B200_TRD_LEGACY=1): three launches per column at the global dependencies of dlatrd,
+// Fall-back for what those do not cover (and A/B switch GSCF_B200_TRD_LEGACY=1): three launches per column at the
+// global dependencies of dlatrd,
 //     trd_col_update : a_i <- A(:,i) - V W(i,:)^T - W V(i,:)^T, partial |a_i|^2       (needs w_{i-1})
 //     trd_symv       : y = A22 v_i in 128x128 tiles + partial V^T v, W^T v              (needs v_i)
 //     trd_assemble_w : w_i = tau (y - V (W^T v) - W (V^T v)), partial w^T v             (needs y)
-//   trd_panel.cuh  : the same three steps as group barriers inside one cooperative launch per panel,
-//   trd_cluster.cuh: ... inside one thread-block cluster with DSMEM exchange,
-//   each followed by the deferred rank-2k DMMA GEMM update of the trailing matrix.
+//   followed per panel by the deferred rank-2k DMMA GEMM update of the trailing matrix.
+// (The round-1 persistent-panel and cluster-panel kernels were superseded by the fused kernels and removed.)
+#include <atomic>
+
 #include "eig.cuh"
 #include "gemm.cuh"
 #include "stedc.cuh"
@@ -371,8 +372,6 @@ __global__ void __launch_bounds__(4 * NBQ) larft_kernel(TrdWs ws, const int* __r
 
 }  // namespace
 }  // namespace gscfb
-#include "trd_panel.cuh"
-#include "trd_cluster.cuh"
 #include "trd_fused.cuh"
 #include "trd_fused_blk.cuh"
 namespace gscfb {
@@ -424,6 +423,9 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.Yw = cv.take<double>((size_t)cap * NBQ * n);
 }
 
+int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, int j0, int pw, int batch,
+                    const int* map, cudaStream_t st);
+
 int tridiagonalise_legacy(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                           cudaStream_t st) {
   int nrb_prev_dot = 0;  // row blocks that wrote pdot in the previous K3
@@ -458,18 +460,8 @@ int tridiagonalise_legacy(int n, double* A, int lda, long long sA, const TrdWs& 
       const int m = n - ilast - 1;
       trd_finalize_w<<<dim3(ceil_div(m, RB), batch), RB, 0, st>>>(A, lda, sA, ws, ilast, j0, nrb_prev_dot, map);
       count_launch();
-      // trailing update A22 -= V2 W2^T + W2 V2^T on rows/cols >= j0 + pw
-      const int r0 = j0 + pw, mt = n - r0;
-      phase_mark(PH_TRAILING_GEMM, true, st);
-      GemmParams g = gemm_params(mt, mt, pw, -1.0, A + (size_t)j0 * lda + r0, lda, ws.W + r0, ws.ld, 1.0,
-                                 A + (size_t)r0 * lda + r0, lda);
-      g.sA = sA; g.sB = (long long)ws.ld * NB; g.sC = sA; g.batch_map = map;
-      GSCF_TRY(launch_gemm(false, true, g, batch, mt, mt, st));
-      GemmParams h = gemm_params(mt, mt, pw, -1.0, ws.W + r0, ws.ld, A + (size_t)j0 * lda + r0, lda, 1.0,
-                                 A + (size_t)r0 * lda + r0, lda);
-      h.sA = (long long)ws.ld * NB; h.sB = sA; h.sC = sA; h.batch_map = map;
-      GSCF_TRY(launch_gemm(false, true, h, batch, mt, mt, st));
-      phase_mark(PH_TRAILING_GEMM, false, st);
+      // trailing update A22 -= V2 W2^T + W2 V2^T on rows/cols >= j0 + pw: one rank-2pw GEMM pass
+      GSCF_TRY(trailing_update(n, A, lda, sA, ws, j0, pw, batch, map, st));
       nrb_prev_dot = 0;
     }
     GSCF_CHECK_LAUNCH();
@@ -519,13 +511,11 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
 template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
-  static bool configured = false;
   auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA>;
-  if (!configured) {
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
-  }
+  // function attributes are per device (and this library may drive several GPUs / host threads from one process):
+  // set them on the current device before every launch - two cheap host calls per tridiagonalisation
+  GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G, cnt);
   cfg.blockDim = dim3(T);
@@ -548,12 +538,8 @@ int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaSt
 
 template <int KMAX, int T>
 int tfb_launch_t(const TfbArgs& a, int G, int cnt, size_t smem, cudaStream_t st) {
-  static bool configured = false;
   auto kern = trd_fused_blocked_kernel<KMAX, T>;
-  if (!configured) {
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  // per device
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G, cnt);
   cfg.blockDim = dim3(T);
@@ -608,12 +594,15 @@ int tf_unblocked_below() {
 // earlier phase), d / e / tau offset alike.  prefer_cluster: one 16-CTA cluster per matrix even for a single matrix.
 int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& ws, double* d, double* e, double* tau,
              unsigned* counters, int batch, const int* map, int jstop, bool prefer_cluster, cudaStream_t st) {
-  static int sms = 0, g_single = 0, force_global = 0, solo_ok = 1, t_small = 256, blocked = 1, cb = 1;
-  static bool init = false;
-  if (!init) {
+  static int g_single = 0, force_global = 0, solo_ok = 1, t_small = 256, blocked = 1, cb = 1;
+  static std::atomic<bool> init{false};
+  int sms = 0;
+  {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);  // of the CURRENT device, every call
+  }
+  if (!init.load(std::memory_order_acquire)) {  // environment switches: idempotent, so a race only repeats the parse
     const char* ge = getenv("GSCF_B200_TF_G");
     g_single = ge ? atoi(ge) : 0;
     const char* fg = getenv("GSCF_B200_TF_GLOBAL");
@@ -626,7 +615,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
     blocked = (be && be[0] == '0') ? 0 : 1;
     const char* ce = getenv("GSCF_B200_TF_CLUSTER_BARRIER");
     cb = (ce && ce[0] == '0') ? 0 : 1;
-    init = true;
+    init.store(true, std::memory_order_release);
   }
   constexpr size_t kSmemMax = 220 * 1024;
   int g_smem = 0;  // fewest CTAs with the columns in shared memory
@@ -795,119 +784,21 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
   return GSCF_B200_OK;
 }
 
-// Persistent-panel driver: one cooperative launch per panel + the deferred rank-2k GEMM update.
+// Dispatch: the fused one-launch reduction; the three-kernels-per-column scheme (the dependencies of dlatrd as separate
+// launches + deferred rank-2k DMMA GEMM updates) covers what the fused kernels do not (n < 3, odd leading dimension,
+// n > 8192, no cooperative launch) and stays selectable for A/B runs (GSCF_B200_TRD_LEGACY=1 or GSCF_B200_TRD_FUSED=0).
 int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                    cudaStream_t st) {
-  static int legacy = -1, g_override = 0, capacity = 0;
+  static int legacy = -1;
   if (legacy < 0) {
     const char* env = getenv("GSCF_B200_TRD_LEGACY");
     legacy = (env && env[0] == '1') ? 1 : 0;
-    const char* ge = getenv("GSCF_B200_TRD_G");
-    g_override = ge ? atoi(ge) : 0;
-    int dev = 0, sms = 0, per_sm = 0, coop = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trd_panel_kernel, PT, 0);
-    capacity = sms * per_sm;
-    if (!coop || capacity < 1) legacy = 1;
   }
-  if (legacy || n < 3) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
-  {
+  if (!legacy && n >= 3) {
     const int fs = tridiagonalise_fused(n, A, lda, sA, ws, batch, map, st);
     if (fs >= 0) return fs;
   }
-  // ---- thread-block-cluster path for L2-resident matrices ------------------------------------------
-  static int cluster_mode = -1;  // 1: available, 0: unavailable / disabled
-  if (cluster_mode < 0) {
-    const char* env = getenv("GSCF_B200_TRD_CLUSTER");
-    cluster_mode = (env && env[0] == '0') ? 0 : 1;
-    if (cluster_mode) {
-      if (cudaFuncSetAttribute(trd_cluster_panel_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
-          cudaFuncSetAttribute(trd_cluster_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-                cudaSuccess) {
-        cudaGetLastError();
-        cluster_mode = 0;
-      }
-    }
-  }
-  if (cluster_mode && n <= CL_MAXN) {
-    int C = batch < 4 ? 16 : 8;
-    const char* ce = getenv("GSCF_B200_TRD_CLUSTER_SIZE");
-    if (ce) C = atoi(ce);
-    while (C > 1 && (n + C - 1) / C < 8) C /= 2;  // tiny matrices: fewer CTAs
-    const size_t smem = trd_cluster_smem_bytes(n, C);
-    if ((n + C - 1) / C <= CT && smem <= 200 * 1024) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(C, 1);
-      cfg.blockDim = dim3(CT);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int max_clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&max_clusters, trd_cluster_panel_kernel, &cfg) == cudaSuccess && max_clusters > 0) {
-        for (int j0 = 0; j0 < n - 1; j0 += NB) {
-          const int pw = std::min(NB, n - 1 - j0);
-          const int last_panel = (j0 + pw == n - 1) ? 1 : 0;
-          for (int mat0 = 0; mat0 < batch; mat0 += 32768) {
-            const int cnt = std::min(32768, batch - mat0);
-            cfg.gridDim = dim3(C, cnt);
-            phase_mark(PH_SYMV_SAMPLE, true, st);
-            GSCF_CUDA_TRY(cudaLaunchKernelEx(&cfg, trd_cluster_panel_kernel, A, lda, sA, ws, j0, pw, last_panel,
-                                             map ? map + mat0 : (const int*)nullptr));
-            phase_mark(PH_SYMV_SAMPLE, false, st);
-            count_launch();
-            if (!map && mat0 > 0) return GSCF_B200_ERR_NOT_IMPLEMENTED;  // > 32768 unmapped matrices: not needed
-          }
-          if (!last_panel) GSCF_TRY(trailing_update(n, A, lda, sA, ws, j0, pw, batch, map, st));
-        }
-        return GSCF_B200_OK;
-      }
-      cudaGetLastError();
-    }
-  }
-  const int gmin = ceil_div(n, PT);
-  if (gmin > capacity) return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
-  GSCF_CUDA_TRY(cudaMemsetAsync(ws.bar, 0, (size_t)ws_cap_hint(ws) * sizeof(unsigned), st));
-  int sms = capacity;  // upper bound for one matrix: one CTA per SM is the sweet spot for the barrier
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  unsigned bar_base = 0;
-  for (int j0 = 0; j0 < n - 1; j0 += NB) {
-    const int pw = std::min(NB, n - 1 - j0);
-    const int last_panel = (j0 + pw == n - 1) ? 1 : 0;
-    const int m = n - j0 - 1;
-    const int tiles = ceil_div(m, SR) * ceil_div(m, SC) + ceil_div(m, SR);
-    // single large matrices are bandwidth-bound: 2 CTAs per SM keep enough loads in flight (measured at n = 4096:
-    // 297 / 220 / 189 ms for 0.5 / 1 / 2 CTAs per SM)
-    const int per_mat = batch == 1 ? 2 * sms : std::max(1, sms / std::max(1, std::min(batch, sms)));
-    int G = g_override > 0 ? g_override : std::min(tiles, per_mat);
-    G = std::max(G, gmin);
-    G = std::min(G, std::min(capacity, GMAX));
-    const int per_launch = std::max(1, capacity / G);
-    for (int mat0 = 0; mat0 < batch; mat0 += per_launch) {
-      const int cnt = std::min(per_launch, batch - mat0);
-      double* Aarg = A; int ldaarg = lda; long long sAarg = sA; TrdWs wsarg = ws;
-      int j0arg = j0, pwarg = pw, lastarg = last_panel, mat0arg = mat0;
-      unsigned basearg = bar_base;
-      const int* maparg = map;
-      void* args[] = {&Aarg, &ldaarg, &sAarg, &wsarg, &j0arg, &pwarg, &lastarg, &basearg, &maparg, &mat0arg};
-      phase_mark(PH_SYMV_SAMPLE, true, st);  // id 11 = the persistent panel kernel (bench.py roofline)
-      GSCF_CUDA_TRY(cudaLaunchCooperativeKernel((void*)trd_panel_kernel, dim3(G, cnt), dim3(PT), args, 0, st));
-      phase_mark(PH_SYMV_SAMPLE, false, st);
-      count_launch();
-    }
-    bar_base += 3u * (unsigned)pw * (unsigned)G;
-    if (!last_panel) GSCF_TRY(trailing_update(n, A, lda, sA, ws, j0, pw, batch, map, st));
-  }
-  return GSCF_B200_OK;
+  return tridiagonalise_legacy(n, A, lda, sA, ws, batch, map, st);
 }
 
 // ---- back-transformation ---------------------------------------------------------------------------------------
@@ -1019,12 +910,8 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
     set_last_error("tridiag_dc_syev_batched: workspace missing or too small");
     return GSCF_B200_ERR_INVALID_ARG;
   }
-  static bool cfg = false;
-  if (!cfg) {
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       NBQ * (NBQ + 1) * (int)sizeof(double)));
-    cfg = true;
-  }
+  GSCF_CUDA_TRY(cudaFuncSetAttribute(larft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     NBQ * (NBQ + 1) * (int)sizeof(double)));  // per device: set before every use
   // capacity: derive from the workspace size so that batch_map indices stay in range
   int cap = batch;
   while (tridiag_dc_worksize(n, cap * 2) <= work_bytes && cap < (1 << 20)) cap *= 2;
