@@ -245,34 +245,73 @@ def ncu_traffic(n):
         return None
 
 
-def run_ours(args, w):
-    import torch
+class Job:
+    """Process-wide context of our arm: device, ranks, the optional process group."""
 
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (gscf_b200 has no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+        self.capi_gather = None
+        self.gather_kind = "single rank"
+        if self.world > 1:
+            # the path's only collective through the library's own C ABI (gscf_b200_ensemble_gather: ncclAllGather on the
+            # engine's stream); torch.distributed only carries the 128-byte NCCL id.  Falls back to torch's all_gather.
+            try:
+                from gscf_b200 import ensemble
+
+                self.capi_gather = ensemble.NcclGather()
+                self.gather_kind = "gscf_b200_ensemble_gather (C ABI, ncclAllGather)"
+            except Exception as exc:  # noqa: BLE001
+                self.capi_gather = None
+                self.gather_kind = f"torch.distributed all_gather (C-ABI communicator unavailable: {exc})"
+            ok = torch.tensor([1.0 if self.capi_gather is not None else 0.0], device="cuda")
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+            if float(ok.cpu()) < 1.0 and self.capi_gather is not None:
+                self.capi_gather.close()
+                self.capi_gather = None
+                self.gather_kind = "torch.distributed all_gather (C-ABI communicator unavailable on some rank)"
+
+    def close(self):
+        if self.capi_gather is not None:
+            self.capi_gather.close()
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measure(job, w, steps, warmup, cpu_baseline=True, sample_clocks=False, problems=0):
+    """Time `steps` solves of workload `w` (after `warmup` untimed ones) on this job's GPUs.  Returns the result record
+    on rank 0 (None elsewhere).  Single problems run as one independent replica per rank, ensembles are sharded by problem
+    index (gscf_b200.ensemble.shard_range: no member dropped)."""
     import gscf_b200 as G
+    from gscf_b200 import ensemble as ENS
     from gscf_b200 import lib as L
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (gscf_b200 has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
+    torch, dist, world, rank = job.torch, job.dist, job.world, job.rank
     n, na, nb, aux, m = w["n"], w["na"], w["nb"], w["aux"], w["m"]
-    ensemble = w["P"] > 1
-    # ensembles are sharded (strong scaling of the fixed ensemble); single problems are replicated
-    P_total = args.problems or w["P"]
-    if ensemble:
-        P_local = P_total // world
-        seeds = list(range(rank * P_local, (rank + 1) * P_local))
+    is_ensemble = w["P"] > 1
+    P_total = problems or w["P"]
+    if is_ensemble:
+        lo, hi = ENS.shard_range(P_total, rank, world)
+        seeds = list(range(lo, hi))
     else:
-        P_local = 1
+        lo, hi = rank, rank + 1
         seeds = [rank]
+    P_local = len(seeds)
+    assert P_local >= 1, "more ranks than ensemble members"
     unrestricted = na != nb
     nblk = 2 if unrestricted else 1
 
@@ -286,10 +325,10 @@ def run_ours(args, w):
                                             L.DEVICE, n, n))
         L.check(L.lib.gscf_b200_copy_matrix(H_host[p].data_ptr(), n, L.HOST, fock.core_ptr() + p * ld * n * 8, ld,
                                             L.DEVICE, n, n))
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    flush = job.flush
 
     params = L.Params()
-    L.lib.gscf_b200_default_params(__import__("ctypes").byref(params))
+    L.lib.gscf_b200_default_params(ctypes.byref(params))
     params.diis_n_prev_steps = m
     fn_ptr, ctx = fock.device_callback()
 
@@ -352,76 +391,98 @@ def run_ours(args, w):
                     scf_ms=scf_ms, fock_ms=fock_ms, overlap_ms=ph["overlap"], ph=ph,
                     d2h=C_host.numel() * 8 + w_host.numel() * 8 + e_host.numel() * 8)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(job.local_rank) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
     launches0 = L.lib.gscf_b200_launch_count()
     t_begin = time.perf_counter()
-    steps = [one_step() for _ in range(args.steps)]
+    done = [one_step() for _ in range(steps)]
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t_total = time.perf_counter() - t_begin
     launches = L.lib.gscf_b200_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
 
-    iters_local = float(sum(int(s["iters"].sum()) for s in steps))
-    conv_local = float(sum(int(s["conv"].sum()) for s in steps))
-    dev_s = sum(s["scf_ms"] + s["overlap_ms"] for s in steps) / 1e3       # device time in the SCF path
-    e2e_s = sum(s["wall"] - s["fock_ms"] / 1e3 for s in steps)            # host-buffer wall time, Fock excluded
-    fock_s = sum(s["fock_ms"] for s in steps) / 1e3
+    iters_local = float(sum(int(s["iters"].sum()) for s in done))
+    conv_local = float(sum(int(s["conv"].sum()) for s in done))
+    dev_s = sum(s["scf_ms"] + s["overlap_ms"] for s in done) / 1e3       # device time in the SCF path
+    e2e_s = sum(s["wall"] - s["fock_ms"] / 1e3 for s in done)            # host-buffer wall time, Fock excluded
+    fock_s = sum(s["fock_ms"] for s in done) / 1e3
+    last = done[-1]
     red = torch.tensor([dev_s, e2e_s, t_total, fock_s], dtype=torch.float64, device="cuda")
     tot = torch.tensor([iters_local, conv_local, float(launches)], dtype=torch.float64, device="cuda")
+    per_rank = torch.tensor([float(last["iters"].max()), float(last["iters"].mean()), float(P_local), dev_s],
+                            dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)  # device times: max over ranks
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        pr = [torch.empty_like(per_rank) for _ in range(world)]
+        dist.all_gather(pr, per_rank)
+        per_rank_table = torch.stack(pr).cpu().numpy()
         # the path's only collective: gather per-problem energies / iteration counts / flags
-        last = steps[-1]
-        rec = torch.tensor(np.stack([last["e"], last["iters"].astype(float), last["conv"].astype(float)], 1),
-                           dtype=torch.float64, device="cuda")
-        gathered = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(gathered, rec)
-        ensemble_table = torch.cat(gathered).cpu().numpy()
+        if is_ensemble and job.capi_gather is not None:
+            rec = job.capi_gather.gather(eng, P_total)              # P_total x (E, ||e||, n_iter, converged, status)
+            ensemble_table = np.stack([rec[:, 0], rec[:, 2], rec[:, 3]], 1)
+        else:
+            local = ENS.pack_records(last["e"], eng.error_norm(), last["iters"], last["conv"], eng.status())
+            if is_ensemble:
+                rec = ENS.gather_records(local, P_total)
+            else:  # replicas: one record per rank
+                rec = ENS.gather_records(local, world)
+            ensemble_table = np.stack([rec[:, 0], rec[:, 2], rec[:, 3]], 1)
     else:
-        last = steps[-1]
+        per_rank_table = per_rank.cpu().numpy()[None]
         ensemble_table = np.stack([last["e"], last["iters"].astype(float), last["conv"].astype(float)], 1)
     dev_s, e2e_s, t_total, fock_s = [float(x) for x in red.cpu()]
     iters_all, conv_all, launches_all = [float(x) for x in tot.cpu()]
 
+    line = None
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
-        ph = steps[-1]["ph"]
+        ph = last["ph"]
         # dominant kernel: the fused one-launch Householder tridiagonalisation (trd_fused.cuh; phase id 11 brackets
-        # its launches on the engine's stream); ensembles of small problems run the shared-memory Jacobi kernel
+        # its launches on the engine's stream)
         roofline = None
-        n_eig = int(steps[-1]["iters"].max())
+        n_eig = int(last["iters"].max())
         if ph["counts"].get("panel_kernel", 0) > 0:
             launches_k = ph["counts"]["panel_kernel"]
             avg_s = ph["panel_kernel"] / 1e3 / launches_k
             # algorithmic bytes: the product with the trailing matrix must read one triangle of it per column,
             # 4 (n-i-1)^2 bytes, from wherever the matrix lives.  For n <= ~1500 the kernel keeps
-            # the matrix in shared memory, so DRAM traffic (`traffic`, from ncu) is only ~12 n^2 bytes and the kernel
-            # is bound by its one L2 exchange per column, not by bandwidth.
+            # the matrix in registers / shared memory, so DRAM traffic (`traffic`, from ncu) is only ~8 n^2 bytes and the
+            # kernel is bound by its one L2 exchange per column, not by bandwidth: see latency_model.
             total_bytes = sum(4.0 * (n - i - 1) ** 2 for i in range(n - 1)) * nblk * P_local
             per_launch = total_bytes * n_eig / launches_k  # n_eig tridiagonalisations in the solve loop
             ach = per_launch / avg_s / 1e9
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            mats_in_flight = max(1, min(P_local * nblk, 148))
             roofline = {"kernel": "trd_fused_kernel (one-launch Householder tridiagonalisation: rank-2 update fused "
                                   "with the trailing-matrix product, one L2 exchange per column)", "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": ncu_traffic(n),
                         "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches_per_solve": launches_k,
-                        "share_of_scf_path": ph["panel_kernel"] / max(1e-9, steps[-1]["scf_ms"])}
+                        "share_of_scf_path": ph["panel_kernel"] / max(1e-9, last["scf_ms"]),
+                        "latency_model": {
+                            "what": "the matrix never leaves the SMs for n <= ~1500, so the HBM fraction measures the "
+                                    "serial chain of n-1 column steps, not traffic; the floor of a column step is the "
+                                    "cross-CTA all-gather of y through L2",
+                            "cycles_per_column": avg_s * sm_mhz * 1e6 / max(1, n - 1) if P_local * nblk == 1 else None,
+                            "exchange_floor_cycles": 2300,
+                            "exchange_floor_source": "scripts/micro/exchange.cu on B200: ~4 dependent L2 round trips "
+                                                     "(3600 cycles for 148 CTAs with fence + atomic + poll)",
+                            "sm_mhz": sm_mhz, "matrices_in_flight": mats_in_flight}}
             if n > 1664 + 128 and P_local * nblk == 1:
                 roofline["launch_note"] = ("one 'launch' = one tridiagonalisation = two kernels: the L2/HBM kernel down "
                                            "to trailing order 1664, then the shared-memory kernel (hand-over); "
                                            "traffic is the ncu figure of the first kernel only")
         flops_it = 7.0 * n ** 3 + 10.0 * n * n * na
-        fp64_tf = flops_it * (iters_all / args.steps / world) * nblk / (dev_s / args.steps) / 1e12 if dev_s > 0 else 0.0
+        fp64_tf = flops_it * (iters_all / steps / world) * nblk / (dev_s / steps) / 1e12 if dev_s > 0 else 0.0
         # FP64 roofline of the whole iteration: LAPACK-equivalent flops W_it = 7 n^3 + 10 n^2 o per rank
         # against the DMMA peak measured on this GPU by a register-resident mma.sync.m8n8k4.f64 loop (outside the timed
         # region; MEASURED_PEAKS.json only has bf16 and HBM)
@@ -430,49 +491,104 @@ def run_ours(args, w):
         if L.lib.gscf_b200_measure_peaks(ctypes.byref(dm), ctypes.byref(df), ctypes.byref(cp)) == L.OK and dm.value > 0:
             fp64_roof = {"bound": "tensor", "achieved": fp64_tf, "peak": dm.value, "unit": "TFLOP/s",
                          "frac": fp64_tf / dm.value, "dfma_peak": df.value,
+                         "peak_source": "builder-measured live (gscf_b200_measure_peaks: register-resident "
+                                        "mma.sync.m8n8k4.f64 loop on this GPU); MEASURED_PEAKS.json has no FP64 figure",
                          "flops_per_iteration": flops_it * nblk, "scope": "whole SCF iteration, per GPU"}
         line = {
             "metric": "scf_iterations_per_s", "value": iters_all / dev_s, "unit": "iterations/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-            "higher_is_better": True, "scaling": "strong" if ensemble else "weak", "vs_baseline": None,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * t_total / steps,
+            "higher_is_better": True, "scaling": "strong" if is_ensemble else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "problems_per_gpu": P_local, "n_bf": n, "n_alpha": na, "n_beta": nb,
-                       "n_aux": aux, "diis_depth": m, "iterations_per_solve": int(steps[-1]["iters"].max()),
-                       "parallelism": ("ensemble sharded by problem index" if ensemble else
+            "config": {"workload": w["desc"], "problems_total": P_total if is_ensemble else world,
+                       "problems_per_gpu": [int(x) for x in per_rank_table[:, 2]] if is_ensemble else 1,
+                       "n_bf": n, "n_alpha": na, "n_beta": nb,
+                       "n_aux": aux, "diis_depth": m, "iterations_per_solve": int(last["iters"].max()),
+                       "parallelism": ("ensemble sharded by problem index (static contiguous blocks, no data-path "
+                                       "collective)" if is_ensemble else
                                        "independent replica per GPU (single problem stays on one GPU)"),
+                       "gather": job.gather_kind,
                        "timing": "value: CUDA-event device time of orthogonaliser set-up + solve loop, Fock builder "
                                  "excluded; e2e: wall clock with host S and guess coefficients in, C/eps/E out, Fock builder excluded",
                        "l2": "256 MiB buffer written between steps (L2 flush)",
-                       "scf_ms_per_step": 1e3 * dev_s / args.steps, "fock_ms_per_step": 1e3 * fock_s / args.steps,
+                       "scf_ms_per_step": 1e3 * dev_s / steps, "fock_ms_per_step": 1e3 * fock_s / steps,
                        "phase_ms_last_step": {k: v for k, v in ph.items() if k != "counts"},
+                       "iterations_per_rank_max_mean": [[float(r[0]), float(r[1])] for r in per_rank_table],
+                       "scf_s_per_rank": [float(r[3]) for r in per_rank_table],
                        "fp64_useful_tflops": fp64_tf, "problems_converged_per_s": conv_all / dev_s,
+                       "problems_converged_per_s_e2e": conv_all / e2e_s,
+                       "converged": int(ensemble_table[:, 2].sum()), "records_gathered": int(ensemble_table.shape[0]),
                        "energies_last_step": [float(x) for x in ensemble_table[:4, 0]]},
             "clocks": clocks,
             "fp64_roofline": fp64_roof,
             "e2e": {"value": iters_all / e2e_s, "unit": "iterations/s",
-                    "h2d_bytes_per_step": int((1 + nblk) * P_local * n * n * 8), "d2h_bytes_per_step": int(steps[-1]["d2h"])},
+                    "h2d_bytes_per_step": int((1 + nblk) * P_local * n * n * 8), "d2h_bytes_per_step": int(last["d2h"])},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            n_it, t_scf, t_fock, e_ref = oracle_time_solve(w if not ensemble else dict(w), seed=seeds[0])
-            line["cpu_baseline"] = {"value": n_it / t_scf, "unit": "iterations/s", "cores": os.cpu_count(),
-                                    "kind": "port",
-                                    "sample": f"1 full DIIS solve ({n_it} iterations) of problem seed {seeds[0]} on the host "
-                                              f"(oracle/: LAPACK dsygvd + dgemm, all BLAS threads); Fock builder excluded",
-                                    "energy_abs_diff_vs_gpu": abs(e_ref - float(steps[-1]["e"][0]))}
-            if ensemble:
+        if world == 1 and cpu_baseline:
+            cores = os.cpu_count() or 1
+            if is_ensemble:
                 # an ensemble's CPU baseline is one member per core, not one member on all cores
-                v, cores, nmem, _ = oracle_time_ensemble(w, seeds[:2 * (os.cpu_count() or 1)])
-                line["cpu_baseline"].update({
-                    "value": v, "cores": cores, "single_problem_all_threads": n_it / t_scf,
+                v, cores, nmem, its_cpu = oracle_time_ensemble(w, seeds[:2 * cores])
+                line["cpu_baseline"] = {
+                    "value": v, "unit": "iterations/s", "cores": cores, "kind": "port",
                     "sample": f"{nmem} members (seeds {seeds[0]}..{seeds[nmem - 1]}), full DIIS solves, one member per core "
-                              f"with BLAS threads = 1 (oracle/: LAPACK dsygvd + dgemm); Fock builder excluded"})
-        print(json.dumps(line))
+                              f"with BLAS threads = 1 (oracle/: LAPACK dsygvd + dgemm); Fock builder excluded"}
+            elif n >= 2048:
+                # bounded sample: 2 DIIS iterations; the SCF path's work per iteration does not depend on n_aux (only the
+                # excluded Fock builder does), so the sample problem is generated with n_aux = 4 to stay within seconds
+                ws = dict(w)
+                ws["aux"] = 4
+                n_it, t_scf, t_fock, _ = oracle_time_solve(ws, seed=seeds[0], max_iter=2)
+                line["cpu_baseline"] = {
+                    "value": n_it / t_scf, "unit": "iterations/s", "cores": cores, "kind": "port",
+                    "sample": f"{n_it} DIIS iterations of problem seed {seeds[0]} generated with n_aux = 4 (same SCF-path work "
+                              f"per iteration) on the host (oracle/: LAPACK dsygvd + dgemm, all BLAS threads); Fock builder excluded"}
+            else:
+                n_it, t_scf, t_fock, e_ref = oracle_time_solve(w, seed=seeds[0])
+                line["cpu_baseline"] = {
+                    "value": n_it / t_scf, "unit": "iterations/s", "cores": cores, "kind": "port",
+                    "sample": f"1 full DIIS solve ({n_it} iterations) of problem seed {seeds[0]} on the host "
+                              f"(oracle/: LAPACK dsygvd + dgemm, all BLAS threads); Fock builder excluded",
+                    "energy_abs_diff_vs_gpu": abs(e_ref - float(last["e"][0]))}
     eng.close()
     fock.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    del S_host, H_host, C_host, G_host
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_ours(args, w):
+    job = Job()
+    headline = measure(job, w, args.steps, args.warmup, cpu_baseline=not args.no_cpu_baseline, sample_clocks=True,
+                       problems=args.problems)
+    extra = {}
+    if args.workload == "c2" and not args.no_workloads:
+        # every other BASELINE configuration under the same clock (bounded: 2 warm-up + 3 timed solves each): the large
+        # single problem on one GPU only (it never leaves one GPU), the ensembles SHARDED over all ranks at every N
+        names = (["c3"] if job.world == 1 else []) + ["c4", "c5"]
+        for name in names:
+            try:
+                rec = measure(job, WORKLOADS[name], 3, 2, cpu_baseline=not args.no_cpu_baseline)
+            except Exception as exc:  # noqa: BLE001 - an extra workload must never take the headline down
+                rec = {"error": repr(exc)} if job.rank == 0 else None
+            if job.rank == 0:
+                extra[name] = rec
+    if job.rank == 0:
+        if extra:
+            keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "e2e",
+                    "gpu_launches", "roofline", "fp64_roofline", "cpu_baseline", "error")
+            headline["workloads"] = {k: {kk: v[kk] for kk in keep if kk in v} for k, v in extra.items()}
+            for k, v in headline["workloads"].items():
+                if "config" in v and WORKLOADS[k]["P"] > 1:
+                    v["metric"] = "problems_converged_per_s"
+                    v["iterations_per_s"] = v["value"]
+                    v["value"] = v["config"]["problems_converged_per_s"]
+                    v["unit"] = "problems/s"
+                    v["e2e"] = dict(v["e2e"], iterations_per_s=v["e2e"]["value"],
+                                    value=v["config"]["problems_converged_per_s_e2e"], unit="problems/s")
+        print(json.dumps(headline))
+    job.close()
 
 
 def main():
@@ -484,6 +600,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--problems", type=int, default=0, help="ensemble size override (c4/c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="headline only: skip the extra BASELINE configurations (c3 / c4 / c5) of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
