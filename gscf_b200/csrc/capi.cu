@@ -143,7 +143,7 @@ int gscf_b200_density(int n, int n_occ, const double* C, int ldc, long long stri
 }
 
 size_t gscf_b200_pulay_error_worksize(int n, int n_occ, int batch) {
-  return (size_t)padded_ld(n) * 2 * (n_occ > 0 ? n_occ : 1) * (size_t)batch * sizeof(double);
+  return pulay_error_work_doubles(n, n_occ) * (size_t)batch * sizeof(double);
 }
 
 int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds, long long strideS,
@@ -151,19 +151,19 @@ int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds
                           double* E, int lde, long long strideE, double* work, long long stride_work, int batch,
                           void* stream) {
   GSCF_TRY(have_device());
-  cudaStream_t st = (cudaStream_t)stream;
-  const int ldw = padded_ld(n);
-  double* SC = work;
-  double* FC = work + (long long)ldw * n_occ;
-  GSCF_TRY(gemm_batched(false, false, n, n_occ, n, 1.0, S, lds, strideS, C, ldc, strideC, 0.0, SC, ldw, stride_work,
-                        batch, nullptr, st));
-  GSCF_TRY(gemm_batched(false, false, n, n_occ, n, 1.0, F, ldf, strideF, C, ldc, strideC, 0.0, FC, ldw, stride_work,
-                        batch, nullptr, st));
-  GSCF_TRY(gemm_batched(false, true, n, n, n_occ, fac, SC, ldw, stride_work, FC, ldw, stride_work, 0.0, E, lde,
-                        strideE, batch, nullptr, st));
-  GSCF_TRY(gemm_batched(false, true, n, n, n_occ, -fac, FC, ldw, stride_work, SC, ldw, stride_work, 1.0, E, lde,
-                        strideE, batch, nullptr, st));
-  return GSCF_B200_OK;
+  if (n < 1 || n_occ < 0 || !S || !F || !C || !E || !work || batch < 0) return GSCF_B200_ERR_INVALID_ARG;
+  if (batch > 1 && stride_work < (long long)pulay_error_work_doubles(n, n_occ)) {
+    set_last_error("pulay_error: stride_work is smaller than gscf_b200_pulay_error_worksize(n, n_occ, 1) / 8");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
+  PulayErrorArgs a{};
+  a.n = n; a.o = n_occ; a.fac = fac;
+  a.S = S; a.lds = lds; a.sS = strideS;
+  a.F = F; a.ldf = ldf; a.sF = strideF;
+  a.C = C; a.ldc = ldc; a.sC = strideC;
+  a.E = E; a.lde = lde; a.sE = strideE;
+  a.work = work; a.swork = stride_work; a.batch = batch; a.batch_map = nullptr;
+  return pulay_error_fused(a, (cudaStream_t)stream);
 }
 
 int gscf_b200_copy_matrix(void* dst, int ld_dst, int dst_loc, const void* src, int ld_src, int src_loc, int rows,

@@ -225,10 +225,10 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
                                0.0, e->Aeig + b * e->mstride, ld);
     h.sA = e->sx_stride ? e->pstride : 0; h.sB = e->pstride; h.sC = e->pstride; h.batch_map = e->act_p;
     h.ktri = tri ? 2 : 0;  // X(i, k) = 0 for k > i
-    h.lower_only = tri ? 1 : 0;  // the eigensolver symmetrises from the lower triangle
+    h.lower_only = tri ? 1 : 0;  // only the tiles on and below the diagonal are computed ...
+    h.mirror = tri ? 1 : 0;      // ... and the epilogue stores every lower entry on both sides: A' exactly symmetric
     GSCF_TRY(launch_gemm(false, false, h, nact, n, n, e->stream));
   }
-  if (tri) GSCF_TRY(symmetrise_from_lower(e->Aeig, ld, e->mstride, n, nm, e->act_m, e->stream));
   const int nv = (e->neig > 0 && e->neig < n) ? e->neig : n;
   GSCF_TRY(syev_batched(e->eig_method, n, e->Aeig, ld, e->mstride, e->orben_cur(), n, e->Zeig, ld,
                         e->mstride, nm, e->act_m, e->eigwork, e->eigwork_bytes, e->eiginfo, e->stream, nv));
@@ -344,27 +344,17 @@ int step_error(Engine* e, int fslot, double* Edst, long long e_pstride, int nact
     return GSCF_B200_OK;
   }
   const double fac = e->nblk == 1 ? 2.0 : 1.0;
-  const long long wstride = (long long)ld * 2 * e->omax;  // per matrix
+  const long long wstride = (long long)pulay_error_work_doubles(n, e->omax);  // per matrix: [SC | FC | FC | -SC]
   for (int b = 0; b < e->nblk; ++b) {
-    const int o = e->occ[b];
-    double* W = e->errwork + b * wstride;  // [SC | FC], each ld x o
-    const double* Sb = e->S + (e->sx_stride ? b * e->mstride : 0);
-    const long long sS = e->sx_stride ? e->pstride : 0;
-    const double* F = e->Fslot(fslot) + b * e->mstride;
-    const double* C = e->Ccur() + b * e->mstride;
-    GemmParams g1 = gemm_params(n, o, n, 1.0, Sb, ld, C, ld, 0.0, W, ld);
-    g1.sA = sS; g1.sB = e->pstride; g1.sC = e->nblk * wstride; g1.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, false, g1, nact, n, o, e->stream));
-    GemmParams g2 = gemm_params(n, o, n, 1.0, F, ld, C, ld, 0.0, W + (long long)ld * o, ld);
-    g2.sA = e->fring_pstride(); g2.sB = e->pstride; g2.sC = e->nblk * wstride; g2.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, false, g2, nact, n, o, e->stream));
-    // E = fac * SC * FC^T - fac * FC * SC^T
-    GemmParams g3 = gemm_params(n, n, o, fac, W, ld, W + (long long)ld * o, ld, 0.0, Edst + b * e->mstride, ld);
-    g3.sA = g3.sB = e->nblk * wstride; g3.sC = e_pstride; g3.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, true, g3, nact, n, n, e->stream));
-    GemmParams g4 = gemm_params(n, n, o, -fac, W + (long long)ld * o, ld, W, ld, 1.0, Edst + b * e->mstride, ld);
-    g4.sA = g4.sB = e->nblk * wstride; g4.sC = e_pstride; g4.batch_map = e->act_p;
-    GSCF_TRY(launch_gemm(false, true, g4, nact, n, n, e->stream));
+    PulayErrorArgs a{};
+    a.n = n; a.o = e->occ[b]; a.fac = fac;
+    a.S = e->S + (e->sx_stride ? b * e->mstride : 0); a.lds = ld; a.sS = e->sx_stride ? e->pstride : 0;
+    a.F = e->Fslot(fslot) + b * e->mstride; a.ldf = ld; a.sF = e->fring_pstride();
+    a.C = e->Ccur() + b * e->mstride; a.ldc = ld; a.sC = e->pstride;
+    a.E = Edst + b * e->mstride; a.lde = ld; a.sE = e_pstride;
+    a.work = e->errwork + b * wstride; a.swork = e->nblk * wstride;
+    a.batch = nact; a.batch_map = e->act_p;
+    GSCF_TRY(pulay_error_fused(a, e->stream));
   }
   return GSCF_B200_OK;
 }
@@ -609,7 +599,7 @@ int gscf_b200_engine_create(const gscf_b200_config* cfg, gscf_b200_engine** out)
   A(&e->Aeig, P * e->pstride);
   A(&e->Zeig, P * e->pstride);
   A(&e->Tmp, P * e->pstride);
-  A(&e->errwork, PM * (size_t)e->ld * 2 * e->omax);
+  A(&e->errwork, PM * pulay_error_work_doubles(e->n, e->omax));
   A(&e->gram, P * e->M * e->M);
   A(&e->coeff, P * kMaxHistory);
   A(&e->dots, P * kMaxHistory);

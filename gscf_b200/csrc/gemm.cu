@@ -66,6 +66,7 @@ dgemm_dmma_kernel(const GemmParams p) {
   const double* A;
   const double* B;
   double* C;
+  double* C2 = nullptr;
   int m, n, k, lda, ldb, ldc;
   double alpha, beta;
   if (p.descs != nullptr) {
@@ -76,6 +77,7 @@ dgemm_dmma_kernel(const GemmParams p) {
     const int ze = p.ksplit > 1 ? blockIdx.z / p.ksplit : blockIdx.z;
     const long long z = p.batch_map ? p.batch_map[ze] : ze;
     A = p.A + z * p.sA; B = p.B + z * p.sB; C = p.C + z * p.sC;
+    if (p.C2) C2 = p.C2 + z * p.sC2;
     m = p.m; n = p.n; k = p.k; lda = p.lda; ldb = p.ldb; ldc = p.ldc;
     alpha = p.alpha; beta = p.beta;
   }
@@ -258,6 +260,33 @@ dgemm_dmma_kernel(const GemmParams p) {
     }
     return;
   }
+  if (p.mirror != 0) {
+    // (anti)symmetric result from the tiles on and below the diagonal: every strictly lower entry is stored twice, the
+    // upper entries a diagonal tile computes are dropped in favour of the mirror images of its lower ones
+    const bool anti = p.mirror < 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int r = m0 + wm + i * 8 + lr;
+      if (r >= m) continue;
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int c = n0 + wn + j * 8 + 2 * lc;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = c + h;
+          if (cc >= n || cc > r) continue;
+          const double v = alpha * acc[i][j][h];
+          if (cc == r) {
+            C[(size_t)cc * ldc + r] = anti ? 0.0 : v;
+          } else {
+            C[(size_t)cc * ldc + r] = v;
+            C[(size_t)r * ldc + cc] = anti ? -v : v;
+          }
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < MI; ++i) {
     const int r = m0 + wm + i * 8 + lr;
@@ -272,6 +301,7 @@ dgemm_dmma_kernel(const GemmParams p) {
           double v = alpha * acc[i][j][h];
           if (beta != 0.0) v += beta * (*dst);
           *dst = v;
+          if (C2) C2[(size_t)(c + h) * p.ldc2 + r] = p.alpha2 * acc[i][j][h];
         }
       }
     }
@@ -342,9 +372,33 @@ int launch_gemm_splitk(bool ta, bool tb, GemmParams p, int batch, int splits, do
   return GSCF_B200_OK;
 }
 
+int pulay_error_fused(const PulayErrorArgs& a, cudaStream_t st) {
+  if (a.batch <= 0 || a.n <= 0) return GSCF_B200_OK;
+  const int n = a.n, o = a.o, ldw = padded_ld(n);
+  // (o == 0: the two skinny products are empty launches and the k = 0 product below stores an all-zero error)
+  double* W = a.work;                               // [S C_o | F C_o]
+  double* W2 = a.work + (size_t)ldw * 2 * o;        // [F C_o | -S C_o]
+  GemmParams g1 = gemm_params(n, o, n, 1.0, a.S, a.lds, a.C, a.ldc, 0.0, W, ldw);
+  g1.sA = a.sS; g1.sB = a.sC; g1.sC = a.swork; g1.batch_map = a.batch_map;
+  g1.C2 = W2 + (size_t)ldw * o; g1.ldc2 = ldw; g1.sC2 = a.swork; g1.alpha2 = -1.0;
+  GSCF_TRY(launch_gemm(false, false, g1, a.batch, n, o, st));
+  GemmParams g2 = gemm_params(n, o, n, 1.0, a.F, a.ldf, a.C, a.ldc, 0.0, W + (size_t)ldw * o, ldw);
+  g2.sA = a.sF; g2.sB = a.sC; g2.sC = a.swork; g2.batch_map = a.batch_map;
+  g2.C2 = W2; g2.ldc2 = ldw; g2.sC2 = a.swork; g2.alpha2 = 1.0;
+  GSCF_TRY(launch_gemm(false, false, g2, a.batch, n, o, st));
+  GemmParams g3 = gemm_params(n, n, 2 * o, a.fac, W, ldw, W2, ldw, 0.0, a.E, a.lde);
+  g3.sA = g3.sB = a.swork; g3.sC = a.sE; g3.batch_map = a.batch_map;
+  g3.lower_only = 1; g3.mirror = -1;
+  return launch_gemm(false, true, g3, a.batch, n, n, st);
+}
+
 int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, int max_n,
                 cudaStream_t st) {
   if (batch <= 0 || max_m <= 0 || max_n <= 0) return GSCF_B200_OK;
+  if (pin.mirror != 0 && (!pin.lower_only || pin.m != pin.n || pin.beta != 0.0 || pin.ksplit > 1 || pin.descs)) {
+    set_last_error("gemm: the mirrored epilogue needs lower_only, a square result, beta == 0 and no split-k / grouping");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
   static int tma = -1;
   if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] == '0') ? 0 : 1; }
   GemmParams p = pin;

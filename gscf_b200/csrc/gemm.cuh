@@ -36,6 +36,13 @@ struct GemmParams {
                           //   1: k < n0 + BN   (op(B)(k, j) = 0 for k > j)      2: k < m0 + BM   (op(A)(i, k) = 0 for k > i)
                           //   3: k >= m0       (op(A)(i, k) = 0 for k < i)
   int lower_only;         // 1: skip tiles strictly above the diagonal (symmetric result, mirrored by the caller)
+  int mirror;             // with lower_only (square C, beta == 0): the epilogue also stores the transposed entry,
+                          //   +1: C(c, r) =  C(r, c)  (symmetric result, replaces a separate symmetrise pass)
+                          //   -1: C(c, r) = -C(r, c), zero diagonal  (antisymmetric result: the Pulay error)
+  double* C2;             // optional second output C2 = alpha2 * op(A) op(B) of the same product (no beta), strided like C
+  int ldc2;
+  long long sC2;
+  double alpha2;
   int use_tma;            // stage interior tiles with TMA bulk copies (set by launch_gemm; GSCF_B200_GEMM_TMA=0 disables)
   int ksplit;             // > 1: split-k, blockIdx.z = entry * ksplit + split, partial tiles go to Cpart
   double* Cpart;          // [batch * ksplit][m * n] partial products (compact, ld = m)
@@ -49,6 +56,7 @@ inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A
   p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
   p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
   p.ksplit = 1; p.Cpart = nullptr; p.ktri = 0; p.lower_only = 0; p.use_tma = 0;
+  p.mirror = 0; p.C2 = nullptr; p.ldc2 = 0; p.sC2 = 0; p.alpha2 = 0.0;
   return p;
 }
 
@@ -75,5 +83,25 @@ inline int gemm_batched(bool ta, bool tb, int m, int n, int k, double alpha, con
   p.sA = sA; p.sB = sB; p.sC = sC; p.batch_map = batch_map;
   return launch_gemm(ta, tb, p, batch, m, n, st);
 }
+
+// Pulay error E = fac [(S C_o)(F C_o)^T - (F C_o)(S C_o)^T]  (src/gscfmock/pulay_error.cc:25-44; fac = 2 closed shell),
+// batched, in three launches and 6 n^2 o flops (the reference's form is four products, 8 n^2 o):
+//   W = [S C_o | F C_o] and W2 = [F C_o | -S C_o] come out of the same two GEMMs (second output of the epilogue),
+//   E = fac W W2^T is ONE k = 2 o product over the tiles on and below the diagonal; the epilogue stores every strictly
+//   lower entry a second time, transposed with the opposite sign, and an exact zero on the diagonal (E is antisymmetric).
+// work: per batch entry ldw x 4 o doubles (ldw = padded_ld(n)), entries stride_work apart.
+struct PulayErrorArgs {
+  int n, o;
+  double fac;
+  const double* S; int lds; long long sS;
+  const double* F; int ldf; long long sF;
+  const double* C; int ldc; long long sC;
+  double* E; int lde; long long sE;
+  double* work; long long swork;
+  int batch;
+  const int* batch_map;
+};
+inline size_t pulay_error_work_doubles(int n, int o) { return (size_t)padded_ld(n) * 4 * (o > 0 ? o : 1); }
+int pulay_error_fused(const PulayErrorArgs& a, cudaStream_t st);
 
 }  // namespace gscfb

@@ -413,6 +413,11 @@ struct ScfBase<State>::Driver {
   static void check(int st) {
     if (st != GSCF_B200_OK) throw b200::Error(st, gscf_b200_last_error());
   }
+  // the engine owns the iteration counters; without a registered hook nobody else keeps the state's count current
+  void sync_iteration_count(state_type& s, int p) {
+    std::vector<int> its(states.size(), 0);
+    if (gscf_b200_get_n_iter(eng, its.data()) == GSCF_B200_OK) s.set_iteration_count((size_t)its[p]);
+  }
   // C: [nblk] n x n column-major, w: [nblk][n]  ->  the state's eigensolution.  Unrestricted: nblk * n vectors of
   // nblk * n elements, alpha block first, zero outside the own block (how lazyten hands out block-diagonal eigenpairs,
   // cf. the index ranges of TruncatedOptDampScf.hh:300-345).
@@ -439,12 +444,7 @@ struct ScfBase<State>::Driver {
     Driver* d = static_cast<Driver*>(ctx);
     try {
       state_type& s = *d->states[p];
-      if (d->states.size() > 1) {  // ensembles: no hook keeps the iteration count current
-        int it = 0;
-        std::vector<int> its(d->states.size());
-        if (gscf_b200_get_n_iter(d->eng, its.data()) == GSCF_B200_OK) it = its[p];
-        s.set_iteration_count((size_t)it);
-      }
+      d->sync_iteration_count(s, p);
       d->mirror_eigensolution(s, p, C, w, (int)s.n_iter());
       if (s.problem_matrix_ptr.use_count() > 1)
         s.problem_matrix_ptr = std::make_shared<probmat_type>(*s.problem_matrix_ptr);
@@ -472,6 +472,7 @@ struct ScfBase<State>::Driver {
     Driver* d = static_cast<Driver*>(ctx);
     try {
       state_type& s = *d->states[p];
+      d->sync_iteration_count(s, p);
       d->mirror_eigensolution(s, p, C, w, (int)s.n_iter());
       const matrix_type e = d->solver->calculate_error(s);
       const size_t N = (size_t)nb * nblocks;

@@ -116,7 +116,10 @@ int gscf_b200_density(int n, int n_occ, const double* C, int ldc, long long stri
                       int ldd, long long strideD, int batch, void* stream);
 
 /* Pulay error e = fac*[(S C_o)(F C_o)^T - (F C_o)(S C_o)^T] (pulay_error.cc:25-44, fac = 2
- * closed shell).  work: n x 4*n_occ doubles per batch entry (ld n rounded to 16). */
+ * closed shell): two skinny products that write [S C_o | F C_o] and [F C_o | -S C_o], then ONE
+ * rank-2*n_occ product over the lower tiles whose epilogue stores the antisymmetric mirror image
+ * (6 n^2 n_occ flops instead of the reference's 8).  work: gscf_b200_pulay_error_worksize bytes
+ * (padded_ld(n) x 4*n_occ doubles per batch entry, stride_work doubles apart). */
 int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds,
                           long long strideS, const double* F, int ldf, long long strideF,
                           const double* C, int ldc, long long strideC, double* E, int lde,

@@ -210,6 +210,37 @@ def test_density_and_pulay_error(env, n, o):
     assert np.abs(D - Cm[:, :o] @ Cm[:, :o].T).max() < 1e-12 * o
     ref = pulay_error(F[None], Cm[None], S, o, o)[0]
     assert np.abs(E - ref).max() < 1e-11 * np.abs(ref).max()
+    # the fused product stores every strictly lower entry twice with opposite signs: exactly antisymmetric, zero diagonal
+    assert np.array_equal(E, -E.T) and not np.any(np.diag(E))
+
+
+@pytest.mark.parametrize("n,o,batch", [(70, 9, 5), (257, 33, 3)])
+def test_pulay_error_batched(env, n, o, batch):
+    """The strided-batch form of gscf_b200_pulay_error (one S shared, F / C / E / work per entry), edge tiles in both
+    tile sizes, against pulay_error.cc:25-44 restated in the oracle."""
+    torch, L = env
+    from oracle import pulay_error
+
+    rng = np.random.default_rng(7 * n + batch)
+    ld = L.lib.gscf_b200_padded_ld(n)
+    S = rng.standard_normal((n, n)); S = S @ S.T / n + np.eye(n)
+    Fs = [(lambda a: a + a.T)(rng.standard_normal((n, n))) for _ in range(batch)]
+    Cs = [rng.standard_normal((n, n)) for _ in range(batch)]
+    dS = dev(torch, colmajor(S, ld))
+    dF = dev(torch, np.concatenate([colmajor(f, ld) for f in Fs]))
+    dC = dev(torch, np.concatenate([colmajor(c, ld) for c in Cs]))
+    dE = torch.full((batch * ld * n,), 7.0, dtype=torch.float64, device="cuda")
+    wsz = L.lib.gscf_b200_pulay_error_worksize(n, o, batch)
+    work = torch.zeros(wsz // 8, dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_pulay_error(n, o, 1.0, dS.data_ptr(), ld, 0, dF.data_ptr(), ld, ld * n, dC.data_ptr(), ld,
+                                        ld * n, dE.data_ptr(), ld, ld * n, work.data_ptr(), wsz // 8 // batch, batch, None))
+    torch.cuda.synchronize()
+    Eall = dE.cpu().numpy()
+    for b in range(batch):
+        E = from_colmajor(Eall[b * ld * n:(b + 1) * ld * n], n, n, ld)
+        ref = 0.5 * pulay_error(Fs[b][None], Cs[b][None], S, o, o)[0]  # the oracle's closed-shell factor 2 taken out
+        assert np.abs(E - ref).max() < 1e-11 * np.abs(ref).max()
+        assert np.array_equal(E, -E.T)
 
 
 def test_measure_peaks_runs(env):
