@@ -37,7 +37,9 @@ constexpr int TF_CG = 8;     // columns per register group in the sweep (indepen
 
 struct TfArgs {
   double* A; int lda; long long sA;
-  double* X;             // [cap][2][2 np] exchange slots (parity of the step): y at [c], raw column j+1 at [np + r]
+  double* X;             // [cap][2][xstride / 2] exchange slots (parity of the step): y at [c], raw column j+1 at
+                         // [np + r], SYMH: row partials of CTA g at [(2 + g) np + r]
+  long long xstride;     // doubles per matrix in X (>= 2 (2 + TF_SYMH_MAXG) np)
   unsigned* ctr;         // [cap] arrival counters, zero on entry
   double *d, *e, *tau;   // [cap][n]
   unsigned* abort_flag;  // one word, zero on entry
@@ -91,7 +93,8 @@ __device__ __forceinline__ double tf_block_sum(double v, double* red) {
   return s;
 }
 
-inline long long tf_x_doubles(int n) { return 4LL * ((n + 1) & ~1); }
+constexpr int TF_SYMH_MAXG = 8;  // largest group of the symmetric-half variant (every CTA publishes a row-partial vector)
+inline long long tf_x_doubles(int n) { return 2LL * (2 + TF_SYMH_MAXG) * ((n + 1) & ~1); }
 inline int tf_smax(int n, int G) { return round_up(ceil_div(n, G), 8); }
 inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
   const int np = round_up(n, 2);
@@ -107,15 +110,24 @@ inline size_t tf_smem_bytes(int n, int G, bool smem_a) {
 // three vectors.  Thread t owns rows 2 (t + T p), 2 (t + T p) + 1, p < RP = 1024 / (2 T), of every owned column.
 constexpr int TF_RS = 8;  // owned columns per CTA in registers
 constexpr int TF_RROWS = 1024;  // rows covered by the register variant: row pairs per thread = TF_RROWS / (2 T)
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
+// SYMH (symmetric half, groups of <= TF_SYMH_MAXG CTAs working in L2 - batches of mid-size matrices, the C5 kernel): the
+// sweep only touches the LOWER triangle of my columns (rows r >= c), i.e. half the L2 traffic of the full-column sweep
+// (8 instead of 16 bytes per trailing-matrix element and column).  Element A(r, c), r > c, then serves both
+//   y_c += A(r, c) v_r   (column part: reduced over the rows, published by the owner of column c as before)   and
+//   y_r += A(r, c) v_c   (row part: accumulated in the registers of the thread that owns row r - no reduction - and
+//                         published as one n-vector per CTA; every CTA adds the G vectors after the SAME exchange).
+// The stale upper triangle is never read as data.
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false>
 __global__ void __launch_bounds__(T, 1)
 trd_fused_kernel(const TfArgs a) {
+  static_assert(!SYMH || (!SMEM_A && !SOLO && !REGA), "SYMH is a variant of the global-memory sweep");
   const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = T / 32;
   const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
   const int n = a.n, lda = a.lda, np = (n + 1) & ~1;
   double* __restrict__ A = a.A + q * a.sA;
-  double* X = a.X + q * 4LL * np;
+  double* X = a.X + q * a.xstride;
+  const long long xhalf = a.xstride >> 1;
   unsigned* ctr = a.ctr + q;
 
   extern __shared__ __align__(16) double tf_smem[];
@@ -189,10 +201,93 @@ trd_fused_kernel(const TfArgs a) {
       const int s0 = first > g ? (first - g + G - 1) / G : 0;
       const int r_lo = first & ~1;
       const int npairs = (np - r_lo) >> 1;
-      double* Xy = X + (size_t)(j & 1) * 2 * np;
+      double* Xy = X + (size_t)(j & 1) * xhalf;
       double* Xr = Xy + np;
       const bool pub_raw = (g + s0 * G == first);  // I own column j+1: its updated values are the raw column
-      if (REGA) {
+      if (SYMH) {
+        constexpr int KP = (KMAX + 1) / 2;  // row pairs per thread
+        double2 rowacc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) rowacc[k] = make_double2(0.0, 0.0);
+        for (int sg = s0; sg < S; sg += TF_CG) {
+          double acc[TF_CG], wc[TF_CG], vc[TF_CG], vjc[TF_CG];
+          int cu[TF_CG];
+#pragma unroll
+          for (int u = 0; u < TF_CG; ++u) {
+            const int slot = sg + u;
+            const int c = g + slot * G;
+            acc[u] = 0.0;
+            cu[u] = slot < S ? c : 0x3fffffff;     // beyond my columns: every row is "above the diagonal"
+            wc[u] = slot < S ? sw[c] : 0.0;    // w_{j-1}(c)
+            vc[u] = slot < S ? svn[c] : 0.0;   // v_{j-1}(c)
+            vjc[u] = slot < S ? svc[c] : 0.0;  // v_j(c)
+          }
+          // rows above the first column of the group are above the diagonal of all its columns
+          const int p_start = max(0, (((g + sg * G) & ~1) - r_lo) >> 1);
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+            const int p = tid + k * T;
+            if (p >= p_start && p < npairs) {
+              const int r = r_lo + 2 * p;
+              const double2 vp = *reinterpret_cast<const double2*>(svn + r);  // v_{j-1}
+              const double2 wp = *reinterpret_cast<const double2*>(sw + r);   // w_{j-1}
+              const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
+              double2 av[TF_CG];
+#pragma unroll
+              for (int u = 0; u < TF_CG; ++u)
+                if (sg + u < S) av[u] = *reinterpret_cast<const double2*>(A + (size_t)(g + (sg + u) * G) * lda + r);
+              const bool odd_tail = (r + 1 >= n);
+#pragma unroll
+              for (int u = 0; u < TF_CG; ++u) {
+                if (sg + u < S && r + 1 >= cu[u]) {  // at least one of the two rows is on or below the diagonal
+                  double* col = A + (size_t)(g + (sg + u) * G) * lda;
+                  double2 x = av[u];
+                  x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+                  x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+                  if (odd_tail) {
+                    x.y = 0.0;
+                    col[r] = x.x;
+                  } else {
+                    *reinterpret_cast<double2*>(col + r) = x;
+                  }
+                  if (pub_raw && sg + u == s0) *reinterpret_cast<double2*>(Xr + r) = x;
+                  const bool d0 = r >= cu[u];                      // (r, c) on or below the diagonal; (r + 1, c) always is
+                  acc[u] = fma(d0 ? x.x : 0.0, vn.x, fma(x.y, vn.y, acc[u]));
+                  rowacc[k].x = fma(r > cu[u] ? x.x : 0.0, vjc[u], rowacc[k].x);
+                  rowacc[k].y = fma(r + 1 > cu[u] ? x.y : 0.0, vjc[u], rowacc[k].y);
+                }
+              }
+            }
+          }
+          {
+            static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
+            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+            double a4[4], a2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+            if ((lane & 3) == 0 && sg + u < S) spart[warp * smax + sg + u] = a1;
+          }
+        }
+        // my row partials (complete over my columns, no reduction needed): one n-vector per CTA
+        double* Xrow = Xy + (size_t)(2 + g) * np;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          const int p = tid + k * T;
+          if (p < npairs) tf_st2(Xrow + r_lo + 2 * p, rowacc[k].x, rowacc[k].y);
+        }
+      } else if (REGA) {
         static_assert(!REGA || TF_RS == TF_CG, "one register group");
         double acc[TF_CG], wc[TF_CG], vc[TF_CG];
 #pragma unroll
@@ -434,6 +529,9 @@ trd_fused_kernel(const TfArgs a) {
         const bool need = r >= first && r < n;
         yv[k] = need ? (SOLO ? sy[r] : tf_ld(Xy + r)) : 0.0;
         rv[k] = need ? (SOLO ? sraw[r] : tf_ld(Xr + r)) : 0.0;
+        if (SYMH && need) {  // + the row parts of every CTA of the group, in a fixed order (bit-identical in all CTAs)
+          for (int g2 = 0; g2 < G; ++g2) yv[k] += tf_ld(Xy + (size_t)(2 + g2) * np + r);
+        }
       }
     }
     TF_TICK(3);

@@ -44,7 +44,8 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
   const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
   const int n = a.n, lda = a.lda, np = (n + 1) & ~1;
   double* __restrict__ A = a.A + q * a.sA;
-  double* X = a.X + q * 4LL * np;
+  double* X = a.X + q * a.xstride;
+  const long long xhalf = a.xstride >> 1;
   unsigned* ctr = a.ctr + q;
   unsigned* ctr2 = ab.ctr2 + q;
   double* VP = ab.VP + q * (long long)PW * np;
@@ -137,7 +138,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
       se = max(s0, min(S, se));
       const int r_lo = first & ~1;
       const int npairs = (np - r_lo) >> 1;
-      double* Xy = X + (size_t)(j & 1) * 2 * np;
+      double* Xy = X + (size_t)(j & 1) * xhalf;
       double* Xr = Xy + np;
       const bool pub_raw = (g + s0 * G == first);
       double* PQs = PQ + (size_t)(nA & 1) * G * 2 * PW;

@@ -410,7 +410,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
   ws.amax = cv.take<unsigned long long>((size_t)cap);
   ws.ascale = cv.take<double>((size_t)cap);
-  ws.X = cv.take<double>((size_t)cap * 4 * round_up(n, 2));
+  ws.X = cv.take<double>((size_t)cap * tf_x_doubles(n));
   ws.p12 = cv.take<double>((size_t)cap * ws.nrb * 2 * NB);
   ws.scal = cv.take<double>((size_t)cap * 8);
   ws.nbw = n <= 256 ? 64 : NBQ;
@@ -509,9 +509,9 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 }
 
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
-  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA>;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA, SYMH>;
   // function attributes are per device (and this library may drive several GPUs / host threads from one process):
   // set them on the current device before every launch - two cheap host calls per tridiagonalisation
   GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -658,7 +658,12 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   const size_t smem = tf_smem_bytes(n, G, smem_a && !rega);
   static int t_big = -1;
   if (t_big < 0) { const char* tb = getenv("GSCF_B200_TF_TBIG"); t_big = tb ? atoi(tb) : 0; }
-  const int T = smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : ((n <= 4096 && t_big != 1024) ? 512 : 1024);
+  // symmetric-half sweep (trd_fused.cuh SYMH): the small-cluster-in-L2 configuration of batches of mid-size matrices
+  static int symh_ok = -1;
+  if (symh_ok < 0) { const char* sh = getenv("GSCF_B200_TF_SYMH"); symh_ok = (sh && sh[0] == '0') ? 0 : 1; }
+  const bool symh = symh_ok && cluster && !smem_a && !solo && G <= TF_SYMH_MAXG && jstop == 0 && n <= 2048;
+  const int T = symh ? 256
+                     : (smem_a ? ((t_small == 128 && n <= 1024) ? 128 : 256) : ((n <= 4096 && t_big != 1024) ? 512 : 1024));
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
@@ -684,6 +689,11 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
       if (rega_t == 512) return tf_launch<2, false, 512, false, true>(a, G, cnt, cluster, smem, st);
       return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
     }
+    if (symh) {  // small clusters in L2, lower triangle only
+      if (K <= 2) return tf_launch<2, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
+      if (K <= 4) return tf_launch<4, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
+      return tf_launch<8, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
+    }
     if (smem_a) {
       if (T == 128) return tf_launch<8, true, 128>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, true, 256>(a, G, cnt, cluster, smem, st);
@@ -702,7 +712,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
     if (mc < 1) return -1;
   }
   TfArgs a;
-  a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.d = d; a.e = e; a.tau = tau; a.dstride = n_full;
+  a.A = A; a.lda = lda; a.sA = sA; a.X = ws.X; a.xstride = tf_x_doubles(n_full); a.d = d; a.e = e; a.tau = tau; a.dstride = n_full;
   a.abort_flag = ws.bar + 4 * ws.cap; a.ctr = counters; a.map = map; a.mat0 = 0; a.n = n; a.smax = tf_smax(n, G);
   a.jstop = jstop;
   a.cluster = (cluster && cb) ? 1 : 0;

@@ -337,7 +337,12 @@ def test_syev_special_matrices(env, n):
     (130, 5, {}),                                                                   # one CTA per matrix (SOLO, shared memory)
     (101, 6, {}),                                                                   # one CTA per matrix, registers
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
-    (1024, 2, {"GSCF_B200_TRD_FUSED": "0"}),                                        # previous panel kernels still work
+    (512, 16, {}),                                                                  # clusters of 4 in L2, lower triangle only (SYMH)
+    (512, 16, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # SYMH with the L2 counter exchange
+    (401, 30, {}),                                                                  # SYMH, odd order
+    (1000, 20, {}),                                                                 # SYMH, four rows per thread
+    (512, 16, {"GSCF_B200_TF_SYMH": "0"}),                                          # clusters of 4 in L2, full-column sweep
+    (1024, 2, {"GSCF_B200_TRD_FUSED": "0"}),                                        # three-kernels-per-column fall-back
     (2048, 1, {}),                                                                  # L2 kernel, hand-over to shared memory
     (1801, 1, {}),                                                                  # shortest L2 phase (136 columns), odd order
     (2601, 1, {}),                                                                  # deferred updates, unblocked, hand-over
