@@ -196,6 +196,30 @@ jacobi_onesided_kernel(const double* __restrict__ Ain, int lda, long long stride
     if (lane == 0) lam[c] = (nrm - sigma) * ascale;
   }
   __syncthreads();
+  // ---- eigenvalues refined as Rayleigh quotients z^T A z with the ORIGINAL matrix -----------------------------
+  // A column norm minus sigma carries the rounding of numbers of size sigma ~ 2 x (Gershgorin radius), an order of
+  // magnitude above eps ||A||_2: harmless for the 1e-9 gate of the DIIS path, but TruncatedOptDampScf forms its line
+  // search from sums of occupied orbital energies (TruncatedOptDampScf.hh:309-319) against total energies, where 1e-14
+  // decides the branch near convergence.  The quotient is accurate to a few eps ||A||_2 (its error is quadratic in
+  // the eigenvector error); the input matrix is still intact in global memory (L2) - n^3 fused multiply-adds.
+  {
+    const double inva = 1.0 / ascale;  // exactly 1 unless the matrix had an extreme norm
+    for (int c = warp; c < n; c += nwarp) {
+      const double* z = G + (size_t)c * ldg;
+      double acc = 0.0;
+      for (int r = lane; r < n; r += 32) {
+        double y = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double a = (r >= k) ? A[(size_t)k * lda + r] : A[(size_t)r * lda + k];
+          y = fma(a * inva, z[k], y);
+        }
+        acc = fma(z[r], y, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0 && isfinite(acc)) lam[c] = acc * ascale;
+    }
+    __syncthreads();
+  }
   // garbage in (NaN / Inf) must be reported, not sorted into a plausible-looking spectrum
   int bad = 0;
   for (int c = tid; c < n; c += nthr) bad |= isfinite(lam[c]) ? 0 : 1;

@@ -117,8 +117,8 @@ constexpr int TF_RROWS = 1024;  // rows covered by the register variant: row pai
 //   y_r += A(r, c) v_c   (row part: accumulated in the registers of the thread that owns row r - no reduction - and
 //                         published as one n-vector per CTA; every CTA adds the G vectors after the SAME exchange).
 // The stale upper triangle is never read as data.
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false>
-__global__ void __launch_bounds__(T, 1)
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1>
+__global__ void __launch_bounds__(T, MINB)
 trd_fused_kernel(const TfArgs a) {
   static_assert(!SYMH || (!SMEM_A && !SOLO && !REGA), "SYMH is a variant of the global-memory sweep");
   const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

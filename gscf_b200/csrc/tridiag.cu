@@ -509,9 +509,9 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 }
 
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
-  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA, SYMH>;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA, SYMH, MINB>;
   // function attributes are per device (and this library may drive several GPUs / host threads from one process):
   // set them on the current device before every launch - two cheap host calls per tridiagonalisation
   GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -690,6 +690,12 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
       return tf_launch<4, false, 256, false, true>(a, G, cnt, cluster, smem, st);
     }
     if (symh) {  // small clusters in L2, lower triangle only
+      // two CTAs per SM (128 registers per thread, a few spilled values) hide the exchange latency of one group behind
+      // the sweep of another: GSCF_B200_TF_SYMH_OCC=2
+      static int occ2 = -1;
+      if (occ2 < 0) { const char* oe = getenv("GSCF_B200_TF_SYMH_OCC"); occ2 = (oe && oe[0] == '2') ? 1 : 0; }
+      if (occ2 && K <= 2) return tf_launch<2, false, 256, false, false, true, 2>(a, G, cnt, cluster, smem, st);
+      if (occ2 && K <= 4) return tf_launch<4, false, 256, false, false, true, 2>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
       if (K <= 4) return tf_launch<4, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
       return tf_launch<8, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);
