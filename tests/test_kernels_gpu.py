@@ -339,6 +339,8 @@ def test_syev_special_matrices(env, n):
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
     (512, 16, {}),                                                                  # clusters of 4 in L2, lower triangle only (SYMH)
     (512, 16, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # SYMH with the L2 counter exchange
+    (512, 16, {"GSCF_B200_TF_SYMH_OCC": "1"}),                                      # SYMH, one CTA per SM build
+    (512, 20, {"GSCF_B200_TF_BATCH_GLOBAL": "2"}),                                  # SYMH, clusters of 2
     (401, 30, {}),                                                                  # SYMH, odd order
     (1000, 20, {}),                                                                 # SYMH, four rows per thread
     (512, 16, {"GSCF_B200_TF_SYMH": "0"}),                                          # clusters of 4 in L2, full-column sweep
