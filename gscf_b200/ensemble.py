@@ -78,13 +78,22 @@ class NcclGather:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         buf = C.create_string_buffer(128)
+        ok, why = 1, ""
         if self.rank == 0:
-            L.check(L.lib.gscf_b200_comm_unique_id(buf))
+            st = L.lib.gscf_b200_comm_unique_id(buf)
+            if st != L.OK:
+                ok, why = 0, L.last_error()
         if self.world > 1:
+            # every rank takes part in this broadcast whatever happened on rank 0 (byte 0 = "rank 0 has an id"), so a
+            # missing NCCL library surfaces as the same exception everywhere instead of a hang
             dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
-            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+            t = torch.frombuffer(bytearray(bytes([ok]) + buf.raw), dtype=torch.uint8).to(dev)
             dist.broadcast(t, src=0, group=group)
-            buf = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+            raw = bytes(t.cpu().numpy().tobytes())
+            ok = raw[0]
+            buf = C.create_string_buffer(raw[1:], 128)
+        if not ok:
+            raise RuntimeError("rank 0 could not create an NCCL unique id: " + (why or "see rank 0"))
         self.handle = C.c_void_p()
         L.check(L.lib.gscf_b200_comm_create(buf, self.world, self.rank, C.byref(self.handle)))
 
