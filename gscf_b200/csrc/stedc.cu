@@ -569,7 +569,10 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
   // a leaf is a serial chain of ~m^2 rotations; measured n = 1024: 5.90 ms with 32, 5.64 ms with 16)
   static int leaf_env = -1;
   if (leaf_env < 0) { const char* le = getenv("GSCF_B200_DC_LEAF"); leaf_env = le ? std::max(4, std::min(kLeaf, atoi(le))) : 0; }
-  const int leaf_target = leaf_env > 0 ? leaf_env : (cap <= 8 ? 16 : kLeaf);
+  // (batches of small matrices: measured at n = 128, whole D&C stage per SCF solve - 4096 matrices 143.5 ms with leaves of 32
+  // against 156.9 ms with 16, 512 matrices 25.3 against 23.0 ms: below ~1000 matrices the serial QL chain of a 32-leaf is
+  // no longer hidden behind other leaves)
+  const int leaf_target = leaf_env > 0 ? leaf_env : ((cap <= 8 || (cap <= 1024 && n <= 256)) ? 16 : kLeaf);
   while (ceil_div(n, 1 << L) > leaf_target) ++L;
   ws.L = L; ws.nleaf = 1 << L;
   ws.lmax = ceil_div(n, 1 << L);

@@ -639,16 +639,25 @@ trd_fused_kernel(const TfArgs a) {
 // ---- single CTA, matrix in registers (n <= 128: the C4 ensemble) ---------------------------------------------------------
 // The shared-memory SOLO variant above re-reads and re-writes the whole trailing matrix through shared memory for every
 // column (n^2 16 bytes at 128 B / clock = 2 000 cycles at n = 128 - measured 3 400 of 5 100 cycles per column).  Here
-// thread (cg = tid / 64, pr = tid % 64) keeps rows 2 pr, 2 pr + 1 of columns cg, cg + 4, ... in 64 registers; a sweep is
-// 192 FMAs per thread on registers plus one 32-value butterfly over the warp.
+// the matrix lives in registers: with NMAX = 128, thread (cg = tid / 64, pr = tid % 64) keeps rows 2 pr, 2 pr + 1 of
+// columns cg, cg + 4, ... (NU = 32 columns, 64 registers); a sweep is 192 FMAs per thread on registers plus one 32-value
+// butterfly over the warp.  The layout is fixed, so the cost of a column step does not shrink with the trailing matrix:
+// NMAX = 64 (thread (cg = tid / 32, pr = tid % 32), columns cg + 8 u, NU = 8) is the same kernel for orders <= 64, and
+// the driver hands the trailing 64 x 64 block of a larger matrix over to it (jstop, see TfArgs) - measured on B200,
+// 4096 matrices of order 128: see DESIGN.md section 5.
+template <int NMAX>
 __global__ void __launch_bounds__(256, 1)
 trd_solo_reg_kernel(const TfArgs a) {
-  constexpr int NMAX = 128, NU = 32;
+  static_assert(NMAX == 128 || NMAX == 64, "layouts: 64 row pairs x 4 column groups, or 32 row pairs x 8 column groups");
+  constexpr int RPAIRS = NMAX / 2;           // row pairs = threads per column group
+  constexpr int NCG = 256 / RPAIRS;          // column groups (4 / 8)
+  constexpr int NU = NMAX / NCG;             // columns per thread (32 / 8)
+  constexpr int WPG = RPAIRS / 32;           // warps per column group (2 / 1)
   __shared__ __align__(16) double sv0[NMAX], sv1[NMAX], sw[NMAX], sraw[NMAX];
   __shared__ double spart[8][NU + 1];
   __shared__ double sred1[8], sred2[8], sbc[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cg = tid >> 6, pr = tid & 63, r0 = 2 * pr;
+  const int cg = tid / RPAIRS, pr = tid % RPAIRS, r0 = 2 * pr;
   const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
   const int n = a.n, lda = a.lda;
   double* __restrict__ A = a.A + q * a.sA;
@@ -656,7 +665,7 @@ trd_solo_reg_kernel(const TfArgs a) {
   double2 ra[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
-    const int c = cg + 4 * u;
+    const int c = cg + NCG * u;
     double2 v = make_double2(0.0, 0.0);
     if (c < n && r0 < n) {
       v.x = A[(size_t)c * lda + r0];
@@ -680,7 +689,8 @@ trd_solo_reg_kernel(const TfArgs a) {
     for (int w = 0; w < 8; ++w) s += red[w];
     return s;
   };
-  for (int j = -1; j <= n - 2; ++j) {
+  const int jlast = (a.jstop > 0 && a.jstop <= n - 2) ? a.jstop - 1 : n - 2;
+  for (int j = -1; j <= jlast; ++j) {
     const int first = j + 1;
     double yv = 0.0, rv = 0.0;  // row r = tid (threads >= n idle in the O(n) part)
     if (j < 0) {
@@ -693,7 +703,7 @@ trd_solo_reg_kernel(const TfArgs a) {
       double acc[NU];
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
-        const int c = cg + 4 * u;
+        const int c = cg + NCG * u;
         double s = 0.0;
         if (c >= first && c < n) {
           const double wc = sw[c], vc = svn[c];
@@ -706,35 +716,62 @@ trd_solo_reg_kernel(const TfArgs a) {
         }
         acc[u] = s;
       }
-      // 32 sums over the 32 lanes: each butterfly step halves the values a lane keeps; lane L ends with the sum of acc[L]
-      double a16[16], a8[8], a4[4], a2[2];
-      {
-        const bool h = lane & 16;
+      if constexpr (NU == 32) {
+        // 32 sums over the 32 lanes: each butterfly step halves the values a lane keeps; lane L ends with the sum of acc[L]
+        double a16[16], a8[8], a4[4], a2[2];
+        {
+          const bool h = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a16[i] = (h ? acc[i + 16] : acc[i]) + __shfl_xor_sync(0xffffffffu, h ? acc[i] : acc[i + 16], 16);
-      }
-      {
-        const bool h = lane & 8;
+          for (int i = 0; i < 16; ++i) a16[i] = (h ? acc[i + 16] : acc[i]) + __shfl_xor_sync(0xffffffffu, h ? acc[i] : acc[i + 16], 16);
+        }
+        {
+          const bool h = lane & 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a8[i] = (h ? a16[i + 8] : a16[i]) + __shfl_xor_sync(0xffffffffu, h ? a16[i] : a16[i + 8], 8);
-      }
-      {
-        const bool h = lane & 4;
+          for (int i = 0; i < 8; ++i) a8[i] = (h ? a16[i + 8] : a16[i]) + __shfl_xor_sync(0xffffffffu, h ? a16[i] : a16[i + 8], 8);
+        }
+        {
+          const bool h = lane & 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a4[i] = (h ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h ? a8[i] : a8[i + 4], 4);
-      }
-      {
-        const bool h = lane & 2;
+          for (int i = 0; i < 4; ++i) a4[i] = (h ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h ? a8[i] : a8[i + 4], 4);
+        }
+        {
+          const bool h = lane & 2;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) a2[i] = (h ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h ? a4[i] : a4[i + 2], 2);
+          for (int i = 0; i < 2; ++i) a2[i] = (h ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h ? a4[i] : a4[i + 2], 2);
+        }
+        const bool h1 = lane & 1;
+        const double tot = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
+        spart[warp][lane] = tot;  // u = lane, rows of this warp (two warps per column group)
+      } else {
+        // 8 sums over the 32 lanes (the warp holds ALL rows of its column group): lanes 0, 4, ... 28 end with column u = lane / 4
+        static_assert(NU == 32 || NU == 8, "butterflies are written for 32 and 8 accumulators");
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+        double a4[4], a2[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+          a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+        if ((lane & 3) == 0) spart[warp][u] = a1;
       }
-      const bool h1 = lane & 1;
-      const double tot = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
-      spart[warp][lane] = tot;  // u = lane, rows of this warp (two warps per column group)
       __syncthreads();
       if (tid < n) {
-        const int c = tid, g4 = c & 3, u = c >> 2;
-        yv = c >= first ? spart[2 * g4][u] + spart[2 * g4 + 1][u] : 0.0;
+        const int c = tid, g4 = c % NCG, u = c / NCG;
+        double y = 0.0;
+        if (c >= first) {
+#pragma unroll
+          for (int w = 0; w < WPG; ++w) y += spart[WPG * g4 + w][u];
+        }
+        yv = y;
         rv = c >= first ? sraw[c] : 0.0;
       }
     }
@@ -775,6 +812,23 @@ trd_solo_reg_kernel(const TfArgs a) {
     __syncthreads();
     double* t = svc; svc = svn; svn = t;
     tau_j = tau_n;
+  }
+  if (jlast < n - 2) {
+    // hand-over: apply the pending reflector jstop-1 (svn = v, sw = w after the last swap) to the trailing block and write
+    // it back; A(jstop:, jstop:) is then the complete (full symmetric) matrix of the remaining reduction
+    const int js = a.jstop;
+    const double2 vp = *reinterpret_cast<const double2*>(svn + r0);
+    const double2 wp = *reinterpret_cast<const double2*>(sw + r0);
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int c = cg + NCG * u;
+      if (c >= js && c < n) {
+        const double wc = sw[c], vc = svn[c];
+        const double2 x = ra[u];
+        if (r0 >= js && r0 < n) A[(size_t)c * lda + r0] = fma(-vp.x, wc, fma(-wp.x, vc, x.x));
+        if (r0 + 1 >= js && r0 + 1 < n) A[(size_t)c * lda + r0 + 1] = fma(-vp.y, wc, fma(-wp.y, vc, x.y));
+      }
+    }
   }
 }
 

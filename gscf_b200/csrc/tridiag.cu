@@ -667,11 +667,14 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   const int K = ceil_div(n, T);
   // (KMAX, SMEM_A, T) instantiations
   auto launch = [&](const TfArgs& a, int cnt) -> int {
-    if (solo && n <= 128 && a.jstop == 0) {
+    if (solo && n <= 128) {
       static int solo_reg = -1;
       if (solo_reg < 0) { const char* sr = getenv("GSCF_B200_TF_SOLO_REG"); solo_reg = (sr && sr[0] == '0') ? 0 : 1; }
       if (solo_reg) {
-        trd_solo_reg_kernel<<<dim3(1, cnt), 256, 0, st>>>(a);
+        // the register layout is fixed per instantiation: orders <= 64 (and the trailing block a larger matrix hands over)
+        // run the 64-row layout, whose column step costs less than half of the 128-row one
+        if (n <= 64) trd_solo_reg_kernel<64><<<dim3(1, cnt), 256, 0, st>>>(a);
+        else trd_solo_reg_kernel<128><<<dim3(1, cnt), 256, 0, st>>>(a);
         count_launch();
         GSCF_CHECK_LAUNCH();
         return GSCF_B200_OK;
@@ -747,8 +750,13 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
 // Returns -1 when the fused kernels do not cover the case (caller falls back to the panel kernels).
 int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                          cudaStream_t st) {
-  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144, handover_on = 1, t_smem = 1664;
+  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144, handover_on = 1, t_smem = 1664, solo_split = 1;
   if (enabled < 0) {
+    const char* sse = getenv("GSCF_B200_TF_SOLO_SPLIT");
+    solo_split = (sse && sse[0] == '0') ? 0 : 1;
+    { const char* sr = getenv("GSCF_B200_TF_SOLO_REG"); if (sr && sr[0] == '0') solo_split = 0; }
+    { const char* so = getenv("GSCF_B200_TF_SOLO"); if (so && so[0] == '0') solo_split = 0; }
+    { const char* fg = getenv("GSCF_B200_TF_GLOBAL"); if (fg && fg[0] == '1') solo_split = 0; }
     const char* env = getenv("GSCF_B200_TRD_FUSED");
     enabled = (env && env[0] == '0') ? 0 : 1;
     int dev = 0, coop = 0, sms = 0;
@@ -778,6 +786,7 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     // a single matrix too large for shared memory: once the trailing block fits (order t_smem on all SMs) hand it to the
     // shared-memory kernel - its sweeps cost half of the L2 ones and its O(n) part handles fewer rows per thread
     if (handover_on && batch == 1 && phase == 0 && ns > t_smem + 128) jstop = (ns - t_smem) & ~1;
+    else if (solo_split && phase == 0 && ns > 96 && ns <= 128) jstop = (ns - 64) & ~1;  // register kernel: 128-row -> 64-row layout
     else if (phases_on && ns <= tf_unblocked_below() && ns <= 2048 && phase < 2) {
       if (t_cluster > t_solo && ns > t_cluster + 64 && batch <= 8) jstop = ns - t_cluster;
       else if (t_solo > 0 && ns > t_solo + 32) jstop = ns - t_solo;

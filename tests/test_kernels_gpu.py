@@ -336,6 +336,12 @@ def test_syev_special_matrices(env, n):
     (512, 12, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # clusters with the L2 counter exchange
     (130, 5, {}),                                                                   # one CTA per matrix (SOLO, shared memory)
     (101, 6, {}),                                                                   # one CTA per matrix, registers
+    (128, 7, {}),                                                                   # registers: 128-row layout, trailing 64 x 64 block handed to the 64-row layout
+    (128, 7, {"GSCF_B200_TF_SOLO_SPLIT": "0"}),                                     # registers: 128-row layout to the end
+    (100, 9, {}),                                                                   # hand-over at column 36
+    (64, 11, {}),                                                                   # 64-row register layout directly
+    (33, 5, {}),                                                                    # 64-row register layout, odd order
+    (128, 40, {"GSCF_B200_DC_LEAF": "32"}),                                         # D&C leaves of 32 (the default above 1024 matrices)
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
     (512, 16, {}),                                                                  # clusters of 4 in L2, lower triangle only (SYMH)
     (512, 16, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # SYMH with the L2 counter exchange
