@@ -619,6 +619,8 @@ class ScfBase:
                 eng.set_hook(hook_cb)
             st = eng.solve(self._method, self._params())
             self._mirror(eng, state)
+            if st == L.ERR_EIGENSOLVER:
+                self._rescue_failed_eigenproblem(eng, state)
             if st != L.OK:
                 msg = L.last_error()
                 state.fail(msg)
@@ -631,6 +633,24 @@ class ScfBase:
         finally:
             eng.close()
         return state
+
+    def _rescue_failed_eigenproblem(self, eng: Engine, state: ScfState):
+        """lazyten::rescue::failed_eigenproblem (ScfBase.hh:334): when the inner eigensolver fails, the eigenproblem that
+        failed is dumped for a post-mortem - here the matrix that was being diagonalised and the overlap, as
+        ``failed_eigenproblem_<pid>.npz`` in the directory named by GSCF_B200_RESCUE_DIR (no dump when unset)."""
+        import os
+
+        d = os.environ.get("GSCF_B200_RESCUE_DIR")
+        if not d:
+            return
+        try:
+            os.makedirs(d, exist_ok=True)
+            path = os.path.join(d, f"failed_eigenproblem_{os.getpid()}.npz")
+            np.savez(path, diagonalised_matrix=eng.get_matrix("diagmat")[0], overlap=np.asarray(state.overlap_matrix()),
+                     n_iter=int(eng.n_iter()[0]))
+            state.rescue_path = path
+        except Exception:  # noqa: BLE001 - a failed dump must not mask the solver exception
+            pass
 
     def _mirror_scalars(self, eng: Engine, state: ScfState):
         e1, e2 = eng.energies()

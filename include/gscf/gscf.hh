@@ -14,6 +14,7 @@
 // state members (rings, coefficients, eigensolutions) are materialised once, after the loop.
 // B200 extension: ScfBase::solve_ensemble runs P independent problems in one engine (lock step).
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -668,9 +669,22 @@ void ScfBase<State>::run_engine(std::vector<state_type*>& states, bool ensemble)
       solver_assert(false, state, lazyten::ExcMaximumNumberOfIterationsReached(this->max_iter));
       break;
     case GSCF_B200_ERR_DIIS_STEP: solver_assert(false, state, ExcDiisStepFailed(gscf_b200_last_error())); break;
-    case GSCF_B200_ERR_EIGENSOLVER:
-      solver_assert(false, state, ExcInnerEigensolverFailed(gscf_b200_last_error()));
+    case GSCF_B200_ERR_EIGENSOLVER: {
+      // lazyten::rescue::failed_eigenproblem (ScfBase.hh:334): dump the eigenproblem that failed (only when the
+      // environment names a directory: GSCF_B200_RESCUE_DIR)
+      const std::string why = gscf_b200_last_error();
+      if (const char* dir = std::getenv("GSCF_B200_RESCUE_DIR")) {
+        std::vector<double> Fd(nblk * n * n), Sd(n * n);
+        if (gscf_b200_get_diagmat(drv.eng, Fd.data(), (int)n) == GSCF_B200_OK) {
+          const overlap_type& S = state.overlap_matrix();
+          for (size_t j = 0; j < n; ++j)
+            for (size_t i = 0; i < n; ++i) Sd[j * n + i] = S(i, j);
+          lazyten::rescue::failed_eigenproblem(std::string(dir), Fd.data(), nblk, Sd.data(), n);
+        }
+      }
+      solver_assert(false, state, ExcInnerEigensolverFailed(why));
       break;
+    }
     default: state.fail(gscf_b200_last_error()); throw b200::Error(st, gscf_b200_last_error());
   }
 }

@@ -6,6 +6,7 @@
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <initializer_list>
 #include <limits>
 #include <memory>
@@ -523,5 +524,27 @@ class IterativeWrapper : public Base {
   }
   void end_iteration_step(state_type& s) const { after_iteration_step(s); }
 };
+
+// rescue::failed_eigenproblem (ScfBase.hh:334): post-mortem dump of an eigenproblem the inner solver could not solve -
+// the matrix blocks and the overlap, column-major, in Mathematica list syntax like lazyten's io writer.
+namespace rescue {
+inline void failed_eigenproblem(const std::string& dir, const double* A, size_t n_blocks, const double* S, size_t n) {
+  const std::string path = dir + "/failed_eigenproblem.m";
+  std::FILE* f = std::fopen(path.c_str(), "w");
+  if (!f) return;
+  auto dump = [&](const char* name, const double* M) {
+    std::fprintf(f, "%s = {", name);
+    for (size_t i = 0; i < n; ++i) {
+      std::fprintf(f, "%s{", i ? "," : "");
+      for (size_t j = 0; j < n; ++j) std::fprintf(f, "%s%.17g", j ? "," : "", M[j * n + i]);
+      std::fprintf(f, "}");
+    }
+    std::fprintf(f, "};\n");
+  };
+  for (size_t b = 0; b < n_blocks; ++b) dump(b == 0 ? "A" : "Abeta", A + b * n * n);
+  dump("S", S);
+  std::fclose(f);
+}
+}  // namespace rescue
 
 }  // namespace lazyten

@@ -643,3 +643,53 @@ def test_chained_diis_then_toda_with_guess(G):
     assert abs(s2.energy_total - o2.energy_total) < TOL_E
     assert abs(s2.energy_total - GOLD["exp_energy_total"]) < GOLD["basetol"]
     assert fock2.n_updates == s2.n_iter() + 1  # one rebuild from the guess, one per iteration
+
+
+def test_chained_toda_then_diis_with_guess(G):
+    """The other hand-over direction (TODA for the first steps, then DIIS, as molsturm does upstream):
+    TruncatedOptDampScf to a loose threshold, PulayDiisScf from its eigensolution through solve_with_guess.  Same chain
+    through the oracle: iteration counts of both legs and the final energy must agree."""
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+    from oracle import pulay_diis_scf, truncated_opt_damp_scf
+    from oracle.mock_fock import IntegralsSturmian14, MockFockProblem
+
+    loose, tight = 1e-2, 5e-7
+    prob = MockFockProblem(IntegralsSturmian14(4.0, GOLD["k_exp"]), 2, 2)
+    F0, e1, e2 = prob.fock(functionality_guess())
+    o1 = truncated_opt_damp_scf(prob, F0, e1, e2, max_error_norm=loose)
+    F1, e1b, e2b = prob.fock(o1.C[0])
+    o2 = pulay_diis_scf(prob, F1, e1b, e2b, n_prev_steps=4, max_error_norm=tight)
+    fock = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    s1 = G.TruncatedOptDampScf({"max_error_norm": loose}).solve(fock, fock.s_bb)
+    fock2 = Sturmian14Fock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    s2 = G.PulayDiisScf({"max_error_norm": tight}).solve_with_guess(fock2, fock2.s_bb, s1)
+    assert s1.n_iter() == o1.n_iter and s2.n_iter() == o2.n_iter
+    assert s2.last_error_norm < tight
+    assert abs(s2.energy_total - o2.energy_total) < TOL_E
+    assert abs(s2.energy_total - GOLD["exp_energy_total"]) < GOLD["basetol"]
+    # DIIS history is NOT transferred (rings start empty, PulayDiisScf.hh:262-269): the first two DIIS iterations are plain
+    assert len(s2.trace_coeff[0]) == 0 and len(s2.trace_coeff[1]) == 1
+
+
+def test_rescue_dump_of_failed_eigenproblem(G, tmp_path, monkeypatch):
+    """lazyten::rescue::failed_eigenproblem (ScfBase.hh:334): a failing inner eigensolver leaves the eigenproblem behind
+    for a post-mortem when GSCF_B200_RESCUE_DIR names a directory."""
+    from gscf_b200 import lib as L
+    from helpers import GOLD, Sturmian14Fock, functionality_guess
+
+    class NanFock(Sturmian14Fock):
+        def as_dense(self):
+            F = np.array(super().as_dense(), dtype=float)
+            F[2, 3] = F[3, 2] = np.nan
+            return F
+
+    monkeypatch.setenv("GSCF_B200_RESCUE_DIR", str(tmp_path))
+    fock = NanFock(GOLD["z_charge"], GOLD["k_exp"], 2, 2, functionality_guess())
+    with pytest.raises((G.ExcInnerEigensolverFailed, L.GscfB200Error)) as ei:
+        G.PlainScf().solve(fock, fock.s_bb)
+    dumps = list(tmp_path.glob("failed_eigenproblem_*.npz"))
+    if isinstance(ei.value, G.ExcInnerEigensolverFailed):
+        assert len(dumps) == 1
+        d = np.load(dumps[0])
+        assert d["diagonalised_matrix"].shape[-2:] == (14, 14) and np.isnan(d["diagonalised_matrix"]).any()
+        assert d["overlap"].shape == (14, 14)
