@@ -150,14 +150,19 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
         const double ei = se[i], di1 = sd[i + 1], di = sd[i];
         __syncwarp();  // every lane has read this step's entries before lane 0 overwrites them
         const double f = sn * ei, b = cs * ei;
-        r = sqrt(fma(f, f, g * g));  // entries are bounded by the leaf's norm; an underflow to 0 takes the exit below
+        // r = sqrt(x), 1 / r as ONE reciprocal square root (1 ulp) and a product: the sqrt + divide chain was a third of
+        // the ~440 cycles of a rotation step, and a leaf is nothing but ~1.5 m^2 such steps in sequence.  Entries are
+        // bounded by the leaf's norm; an underflow of x to 0 takes the exit below.
+        const double x = fma(f, f, g * g);
+        const double rinv = rsqrt(x);
+        r = x * rinv;
+        if (x == 0.0) r = 0.0;
         if (lane == 0) se[i + 1] = r;
         if (r == 0.0) {
           if (lane == 0) { sd[i + 1] = di1 - p; se[mm] = 0.0; }
           underflow = true;
           break;
         }
-        const double rinv = 1.0 / r;
         sn = f * rinv;
         cs = g * rinv;
         g = di1 - p;
