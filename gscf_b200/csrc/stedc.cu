@@ -416,6 +416,35 @@ dc_secular_kernel(StedcWs ws, int h, int lev_out, const int* __restrict__ map) {
   if ((threadIdx.x & 31) == 0) (ws.lam[lev_out] + q * n + lo)[i] = lam;
 }
 
+// One THREAD per root, for batches of many small merges (C4: 4096 x n = 128): with K <= 128 poles a warp per root spends
+// most of its instructions on the four butterfly sums and on scalar work that 32 lanes repeat (measured: the two
+// dc_secular launches of a C4 iteration were 2.6 of 9 ms of its D&C stage).  Poles and z live in shared memory (every lane
+// reads the same entry: broadcast), consecutive threads write consecutive rows of delta.  Same iteration and stopping
+// rule (dc_core.hpp:secular_root, the routine the host unit test checks against dlaed4-style references).
+__global__ void __launch_bounds__(128)
+dc_secular_thread_kernel(StedcWs ws, int h, int lev_out, int kcap, const int* __restrict__ map) {
+  extern __shared__ __align__(16) double ssec[];  // d[kcap] | z[kcap]
+  const int t = blockIdx.y, zb = blockIdx.z;
+  const long long q = map ? map[zb] : zb;
+  const int n = ws.n;
+  const NodeGeom g = node_geom(t, h, n, ws.L);
+  const int lo = g.lo;
+  const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
+  if ((int)(blockIdx.x * blockDim.x) >= K) return;  // whole block beyond the (deflated) problem size
+  double* sd = ssec;
+  double* sz = ssec + kcap;
+  const double* dl = ws.dlamda + q * n + lo;
+  const double* wl = ws.w + q * n + lo;
+  for (int j = threadIdx.x; j < K; j += blockDim.x) { sd[j] = dl[j]; sz[j] = wl[j]; }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const double rho = (ws.rho + (size_t)q * ws.nleaf)[t];
+  double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;  // node block, [j*ld + i]
+  const double lam = secular_root(K, i, sd, sz, rho, S + i, ws.ld, nullptr);
+  (ws.lam[lev_out] + q * n + lo)[i] = lam;
+}
+
 // zhat_j = sign(w_j) sqrt( - delta(j,j) * prod_{i != j} delta(j,i) / (d_j - d_i) )
 __global__ void __launch_bounds__(256)
 dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
@@ -648,7 +677,18 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
     zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[nxt], bufld[nxt], bufs[nxt], n, map);
     dc_prepare_kernel<<<dim3(nodes, batch), 256, use_smem ? smem : 0, st>>>(ws, e, dstride, h, lev, bufp[cur],
                                                                             bufld[cur], bufs[cur], use_smem, map);
-    dc_secular_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, 1 - lev, map);
+    // a warp per root (latency: one large merge) or a thread per root (throughput: many small merges)
+    static int sec_mode = -1;  // 0 auto, 1 warp, 2 thread
+    if (sec_mode < 0) {
+      const char* se = getenv("GSCF_B200_DC_SECULAR");
+      sec_mode = !se ? 0 : (se[0] == 'w' ? 1 : (se[0] == 't' ? 2 : 0));
+    }
+    const bool sec_thread = kmax <= 256 && (sec_mode == 2 || (sec_mode == 0 && (long long)nodes * batch * kmax >= 65536));
+    if (sec_thread)
+      dc_secular_thread_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, (size_t)2 * kmax * sizeof(double), st>>>(
+          ws, h, 1 - lev, kmax, map);
+    else
+      dc_secular_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, 1 - lev, map);
     dc_zhat_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, map);
     dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, map);
     dc_gather_kernel<<<dim3(kmax, nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur],

@@ -341,6 +341,9 @@ def test_syev_special_matrices(env, n):
     (100, 9, {}),                                                                   # hand-over at column 36
     (64, 11, {}),                                                                   # 64-row register layout directly
     (33, 5, {}),                                                                    # 64-row register layout, odd order
+    (128, 40, {"GSCF_B200_DC_SECULAR": "thread"}),                                  # secular equation: one thread per root
+    (512, 12, {"GSCF_B200_DC_SECULAR": "thread"}),                                  # ... up to 256 poles, a warp per root above
+    (257, 9, {"GSCF_B200_DC_SECULAR": "thread", "GSCF_B200_DC_LEAF": "32"}),
     (128, 40, {"GSCF_B200_DC_LEAF": "32"}),                                         # D&C leaves of 32 (the default above 1024 matrices)
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
     (512, 16, {}),                                                                  # clusters of 4 in L2, lower triangle only (SYMH)
