@@ -685,7 +685,7 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
     }
     // (measured at n = 128: 4096 matrices 138.3 -> 128.1 ms per solve with the thread kernel, 512 matrices 22.2 -> 24.7 ms:
     // below ~250k roots per launch the serial K-loop of a thread is no longer hidden)
-    const bool sec_thread = kmax <= 256 && (sec_mode == 2 || (sec_mode == 0 && kmax <= 128 &&
+    const bool sec_thread = kmax <= 256 && (sec_mode == 2 || (sec_mode == 0 && kmax <= 160 &&
                                                               (long long)nodes * batch * kmax >= 262144));
     if (sec_thread)
       dc_secular_thread_kernel<<<dim3(ceil_div(kmax, 128), nodes, batch), 128, (size_t)2 * kmax * sizeof(double), st>>>(
