@@ -39,39 +39,47 @@ chol_diag_kernel(const double* __restrict__ Ab, int lda, long long sA, double* _
     shX[c * CLD + r] = 0.0;
   }
   __syncthreads();
-  // right-looking unblocked Cholesky
-  for (int k = 0; k < nb; ++k) {
-    const double d = shL[k * CLD + k];
-    if (!(d > 0.0)) {
-      if (tid == 0) s_bad = 1;
-    }
-    const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
-    __syncthreads();
-    for (int r = k + tid; r < nb; r += blockDim.x) shL[k * CLD + r] *= inv;  // column k (the diagonal becomes sqrt(d))
-    __syncthreads();
-    const int rem = nb - k - 1;
-    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-      const int cc = idx / rem, rr = idx - cc * rem;
-      if (rr >= cc) {
-        const int c = k + 1 + cc, r = k + 1 + rr;
-        shL[c * CLD + r] = fma(-shL[k * CLD + r], shL[k * CLD + c], shL[c * CLD + r]);
+  // Right-looking unblocked Cholesky with ONE barrier per column: thread (r = tid mod 64, cp = tid / 64) owns row r and
+  // every 4th column of the trailing block; the scaled column k is formed on the fly (1 / L_kk from one reciprocal square
+  // root) and only stored after everybody has used the unscaled one.  (The first version took 108 us per 64 x 64 block -
+  // three barriers, a square root + divide and an integer division per updated element - 16 blocks in sequence were
+  // 1.7 of the 2.9 ms of the n = 1024 set-up.)
+  static_assert(CB == 64, "thread mapping below: 256 threads = 64 rows x 4 column phases");
+  __shared__ double s_rd[CB];  // 1 / L(k, k)
+  {
+    const int r = tid & (CB - 1), cp = tid >> 6;
+    for (int k = 0; k < nb; ++k) {
+      const double d = shL[k * CLD + k];
+      const bool ok = d > 0.0;
+      const double inv = ok ? rsqrt(d) : 0.0;
+      if (!ok && tid == 0) s_bad = 1;
+      const bool mine = r > k && r < nb;
+      const double lrk = mine ? shL[k * CLD + r] * inv : 0.0;
+      if (mine) {
+        for (int c = k + 1 + cp; c <= r; c += 4) {
+          const double lck = shL[k * CLD + c] * inv;
+          shL[c * CLD + r] = fma(-lrk, lck, shL[c * CLD + r]);
+        }
       }
+      __syncthreads();  // every read of the unscaled column k (and of its pivot) is done; column k + 1 is final
+      if (cp == 0 && r >= k && r < nb) shL[k * CLD + r] = (r == k) ? d * inv : lrk;  // L_kk = d / sqrt(d)
+      if (tid == 0) s_rd[k] = inv;
     }
-    __syncthreads();
   }
+  __syncthreads();
   // inverse: column c by forward substitution, one quad of lanes per column
   {
     const int c = tid >> 2, part = tid & 3;
     const unsigned qmask = 0xFu << (tid & 28);
     if (c < nb) {
-      if (part == 0) shX[c * CLD + c] = 1.0 / shL[c * CLD + c];
+      if (part == 0) shX[c * CLD + c] = s_rd[c];
       __syncwarp(qmask);
       for (int r = c + 1; r < nb; ++r) {
         double s = 0.0;
         for (int k = c + part; k < r; k += 4) s = fma(shL[k * CLD + r], shX[c * CLD + k], s);
         s += __shfl_xor_sync(qmask, s, 1);
         s += __shfl_xor_sync(qmask, s, 2);
-        if (part == 0) shX[c * CLD + r] = -s / shL[r * CLD + r];
+        if (part == 0) shX[c * CLD + r] = -s * s_rd[r];
         __syncwarp(qmask);
       }
     }
