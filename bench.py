@@ -330,6 +330,8 @@ def measure(job, w, steps, warmup, cpu_baseline=True, sample_clocks=False, probl
     params = L.Params()
     L.lib.gscf_b200_default_params(ctypes.byref(params))
     params.diis_n_prev_steps = m
+    if w.get("n_eigenpairs"):
+        params.n_eigenpairs = int(w["n_eigenpairs"])  # ScfBaseKeys::n_eigenpairs < n: partial-spectrum eigensolves
     fn_ptr, ctx = fock.device_callback()
 
     eng = G.Engine(n, na, nb, n_blocks=nblk, n_problems=P_local, max_history=max(m, 2))
@@ -600,11 +602,16 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--problems", type=int, default=0, help="ensemble size override (c4/c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n-eigenpairs", type=int, default=0,
+                    help="measurement aid: run the workload with ScfBaseKeys::n_eigenpairs = K < n_bf (default: all)")
     ap.add_argument("--no-workloads", action="store_true",
                     help="headline only: skip the extra BASELINE configurations (c3 / c4 / c5) of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
+    if args.n_eigenpairs:
+        w = dict(w, n_eigenpairs=args.n_eigenpairs,
+                 desc=w["desc"] + f" [n_eigenpairs = {args.n_eigenpairs}: partial-spectrum eigensolves, not the BASELINE config]")
     if args.impl == "reference":
         run_reference(args, w)
     else:

@@ -100,6 +100,22 @@ int gscf_b200_syev(int method, int n, double* A, int lda, long long strideA, dou
                       info_dev, (cudaStream_t)stream);
 }
 
+int gscf_b200_syevx(int method, int n, int n_eigenpairs, double* A, int lda, long long strideA, double* w,
+                    long long stride_w, double* Z, int ldz, long long strideZ, int batch, void* work, size_t work_bytes,
+                    int* info_dev, void* stream) {
+  GSCF_TRY(have_device());
+  if (n_eigenpairs < 1 || n_eigenpairs > n) {
+    set_last_error("syevx: n_eigenpairs must be in [1, n]");
+    return GSCF_B200_ERR_INVALID_ARG;
+  }
+  const int m = resolve_eig_method(method, n);
+  if (m < 0) return GSCF_B200_ERR_INVALID_ARG;
+  if (m == GSCF_B200_EIG_TRIDIAG_DC)
+    GSCF_TRY(symmetrise_from_lower(A, lda, strideA, n, batch, nullptr, (cudaStream_t)stream));
+  return syev_batched(m, n, A, lda, strideA, w, stride_w, Z, ldz, strideZ, batch, nullptr, work, work_bytes,
+                      info_dev, (cudaStream_t)stream, n_eigenpairs);
+}
+
 size_t gscf_b200_frob_multidot_worksize(int count, int rows, int cols, int batch) {
   return multidot_worksize(count, rows, cols, batch);
 }

@@ -20,8 +20,9 @@ struct DcPlan;
 size_t tridiag_dc_worksize(int n, int batch);
 // A (n x n, ld lda, FULL symmetric storage, destroyed) -> w ascending, Z (n x n) eigenvectors.
 // batch_map (optional): entry z works on matrix batch_map[z] of every strided array.
-// nvec: only the eigenvectors of the nvec lowest eigenvalues are back-transformed (n_eigenpairs < n, ScfBase.hh:87);
-// all n eigenvalues are always returned.
+// nvec (n_eigenpairs < n, ScfBase.hh:87): a partial-spectrum solve - the top-level merge of the divide & conquer forms
+// eigenvectors only for the nvec lowest eigenvalues (three quarters of its flops otherwise) and only those nvec vectors are
+// back-transformed; all n eigenvalues are always returned, columns >= nvec of Z are unspecified.
 int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double* w,
                             long long stride_w, double* Z, int ldz, long long strideZ, int batch,
                             const int* batch_map, void* work, size_t work_bytes, int* info_dev,

@@ -445,8 +445,9 @@ int check_ready(Engine* e, const gscf_b200_params* prm) {
   if (!e || !prm) return GSCF_B200_ERR_INVALID_ARG;
   if (!e->have_overlap) { set_last_error("overlap not set"); return GSCF_B200_ERR_INVALID_STATE; }
   if (e->cur_slot < 0) { set_last_error("problem matrix not set"); return GSCF_B200_ERR_INVALID_STATE; }
-  // n_eigenpairs (ScfBase.hh:87, :315-316): the lowest k pairs.  All n eigenvalues are still computed (dense
-  // tridiagonal D&C); what k < n saves is the back-transformation and X Z of the n - k unwanted vectors.
+  // n_eigenpairs (ScfBase.hh:87, :315-316): the lowest k pairs.  All n eigenvalues are still computed (the Gu-Eisenstat
+  // merges need every root); what k < n saves is the eigenvector part of the top-level merge of the divide & conquer,
+  // the back-transformation and X Z of the n - k unwanted vectors.
   e->neig = e->n;
   if (prm->n_eigenpairs >= 0 && prm->n_eigenpairs < e->n) {
     const int kmin = std::max(e->occ[0], e->nblk > 1 ? e->occ[1] : 0);

@@ -472,7 +472,7 @@ dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
 
 // U^T[gpos[j]][i] = zhat_j / delta(j,i) / ||.||.  CTA = 32 eigenvectors (lane) x 8 warps splitting the poles.
 __global__ void __launch_bounds__(256)
-dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
+dc_vectors_kernel(StedcWs ws, int h, int partial, const int* __restrict__ map) {
   __shared__ double snrm[8][33];
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
@@ -480,7 +480,9 @@ dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   const NodeGeom g = node_geom(t, h, n, ws.L);
   const int lo = g.lo;
   const int K = (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[0];
-  if (blockIdx.x * 32 >= K) return;
+  // partial spectrum (top-level merge only): eigenvectors of the first Ksel roots, see dc_select_kernel
+  const int Kv = partial ? (ws.meta + ((size_t)q * ws.nleaf + t) * 8)[5] : K;
+  if (blockIdx.x * 32 >= Kv) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
   const double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
@@ -489,7 +491,7 @@ dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   const int* gpos = ws.gpos + q * n + lo;
   // pass 1: unnormalised components (one division each) into U, norms; pass 2: scale in place (same thread, same entries)
   double nrm = 0.0;
-  if (i < K)
+  if (i < Kv)
     for (int j = warp; j < K; j += 8) {
       const double u = zh[j] / S[(size_t)j * ws.ld + i];
       U[(size_t)gpos[j] * ws.ld + i] = u;
@@ -501,15 +503,46 @@ dc_vectors_kernel(StedcWs ws, int h, const int* __restrict__ map) {
 #pragma unroll
   for (int w = 0; w < 8; ++w) tot += snrm[w][lane];
   const double inv = 1.0 / sqrt(tot);
-  if (i < K)
+  if (i < Kv)
     for (int j = warp; j < K; j += 8) U[(size_t)gpos[j] * ws.ld + i] *= inv;
+}
+
+// Partial spectrum (n_eigenpairs = nvec < n, ScfBase.hh:87,315-316): at the TOP-LEVEL merge only the eigenvectors of
+// the nvec lowest eigenvalues of the whole matrix are wanted.  All K roots are still needed (the Gu-Eisenstat z-hat is a
+// product over every root), but eigenvectors - the K x K matrix U and the Q U products, three quarters of the flops of
+// the whole divide & conquer - only for the roots whose global rank is below nvec.  Roots ascend with their index, so
+// these are the first Ksel roots; the rank counts the deflated eigenvalues below a root (ties: the root first, the order
+// dc_rank_kernel uses).  Ksel goes to meta[5] of the (single) top-level node.
+__global__ void __launch_bounds__(256)
+dc_select_kernel(StedcWs ws, int lev_out, int nvec, const int* __restrict__ map) {
+  __shared__ int s_cnt;
+  const long long q = map ? map[blockIdx.x] : blockIdx.x;
+  const int n = ws.n;
+  int* meta = ws.meta + (size_t)q * ws.nleaf * 8;  // node 0 of the top level
+  const int K = meta[0];
+  const double* lam = ws.lam[lev_out] + q * n;
+  const int* dcol = ws.dcol + q * n;
+  const double* dwork = ws.dwork + q * n;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const long long li = dc_sort_key(lam[i]);
+    int below = 0;
+    for (int tdx = 0; tdx < n - K; ++tdx) below += dc_sort_key(dwork[dcol[tdx]]) < li ? 1 : 0;
+    if (i + below < nvec) ++mine;
+  }
+  if (mine) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) meta[5] = s_cnt;
 }
 
 // Gather non-deflated columns (grouped by type) into Gq, copy deflated columns/eigenvalues to the
 // output, and write the two GEMM descriptors of this merge.
 __global__ void __launch_bounds__(128)
 dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin, int ldin, long long sin,
-                 double* __restrict__ Zout, int ldout, long long sout, int nodes, const int* __restrict__ map) {
+                 double* __restrict__ Zout, int ldout, long long sout, int nodes, int partial,
+                 const int* __restrict__ map) {
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
   const int n = ws.n;
@@ -527,10 +560,11 @@ dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin,
     GemmDesc top, bot;
     top.A = Gq; top.lda = ws.ld; top.B = U; top.ldb = ws.ld;
     top.C = Zo + (size_t)lo * ldout + lo; top.ldc = ldout;
-    top.m = n1; top.n = K; top.k = c1 + c2; top.alpha = 1.0; top.beta = 0.0;
+    const int Kn = partial ? meta[5] : K;  // partial spectrum: only the columns of the selected roots
+    top.m = n1; top.n = Kn; top.k = c1 + c2; top.alpha = 1.0; top.beta = 0.0;
     bot.A = Gq + (size_t)c1 * ws.ld + n1; bot.lda = ws.ld; bot.B = U + (size_t)c1 * ws.ld; bot.ldb = ws.ld;
     bot.C = Zo + (size_t)lo * ldout + lo + n1; bot.ldc = ldout;
-    bot.m = k - n1; bot.n = K; bot.k = c2 + c3; bot.alpha = 1.0; bot.beta = 0.0;
+    bot.m = k - n1; bot.n = Kn; bot.k = c2 + c3; bot.alpha = 1.0; bot.beta = 0.0;
     dsc[0] = top;
     dsc[1] = bot;
   }
@@ -572,14 +606,15 @@ __global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, cons
 
 __global__ void dc_permute_kernel(StedcWs ws, int lev, const double* __restrict__ Zin, int ldin, long long sin,
                                   double* __restrict__ Zout, int ldout, long long sout, double* __restrict__ w,
-                                  long long stride_w, int* __restrict__ info, const int* __restrict__ map) {
+                                  long long stride_w, int* __restrict__ info, int nvec, const int* __restrict__ map) {
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
   const int n = ws.n;
   const int j = blockIdx.x;
   const int r = (ws.rank + q * n)[j];
   const double* x = Zin + q * sin + (size_t)j * ldin;
   double* y = Zout + q * sout + (size_t)r * ldout;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
+  if (r < nvec)  // partial spectrum: the other eigenvectors were never formed
+    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
   if (threadIdx.x == 0) {
     const double l = (ws.lam[lev] + q * n)[j] * ws.scale[q];
     (w + q * stride_w)[r] = l;
@@ -634,9 +669,10 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws) {
 
 int stedc_batched(int n, double* d, double* e, long long dstride, double* w, long long stride_w,
                   double* Z, int ldz, long long strideZ, const StedcWs& ws, int batch, const int* map,
-                  int* info_dev, cudaStream_t st) {
+                  int* info_dev, cudaStream_t st, int nvec) {
   if (batch <= 0) return GSCF_B200_OK;
   const int L = ws.L;
+  const int nv = (nvec > 0 && nvec < n) ? nvec : n;
   const int gx = std::max(1, std::min(148 * 4 / std::max(1, batch), ceil_div(n * n, 256 * 8)));
   // buffers: X_0 (leaf eigenvectors) -> level 1 -> ... -> X_L -> sorted into Z
   // X_L must be the workspace buffer, so X_0 = Zb for even L and Z for odd L.
@@ -693,9 +729,14 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
     else
       dc_secular_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, 1 - lev, map);
     dc_zhat_kernel<<<dim3(ceil_div(kmax, 8), nodes, batch), 256, 0, st>>>(ws, h, map);
-    dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, map);
+    const int partial = (h == L && nv < n) ? 1 : 0;  // top-level merge of a partial-spectrum solve
+    if (partial) {
+      dc_select_kernel<<<batch, 256, 0, st>>>(ws, 1 - lev, nv, map);
+      count_launch();
+    }
+    dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, partial, map);
     dc_gather_kernel<<<dim3(kmax, nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur],
-                                                              bufp[nxt], bufld[nxt], bufs[nxt], nodes, map);
+                                                              bufp[nxt], bufld[nxt], bufs[nxt], nodes, partial, map);
     count_launch(6);
     GSCF_CHECK_LAUNCH();
     GemmParams gp{};
@@ -708,7 +749,7 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
   // ---- final ascending order ----------------------------------------------------------------------------
   dc_rank_kernel<<<dim3(std::max(1, ceil_div(n, 128)), batch), 128, 0, st>>>(ws, lev, info_dev, map);
   dc_permute_kernel<<<dim3(n, batch), 128, 0, st>>>(ws, lev, bufp[cur], bufld[cur], bufs[cur], Z, ldz, strideZ, w,
-                                                    stride_w, info_dev, map);
+                                                    stride_w, info_dev, nv, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   return GSCF_B200_OK;

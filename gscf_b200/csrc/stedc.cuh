@@ -45,6 +45,6 @@ size_t stedc_carve(char* base, size_t offset, int n, int cap, StedcWs& ws);
 // w ascending (stride_w per matrix) and eigenvectors Z (n x n, ldz, strideZ).
 int stedc_batched(int n, double* d, double* e, long long dstride, double* w,
                   long long stride_w, double* Z, int ldz, long long strideZ, const StedcWs& ws,
-                  int batch, const int* batch_map, int* info_dev, cudaStream_t st);
+                  int batch, const int* batch_map, int* info_dev, cudaStream_t st, int nvec = -1);
 
 }  // namespace gscfb

@@ -983,7 +983,7 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
     GSCF_CUDA_TRY(cudaEventRecord(ev_join, side));
   }
   phase_mark(PH_STEDC, true, st);
-  GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st));
+  GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st, nvec));
   phase_mark(PH_STEDC, false, st);
   phase_mark(PH_BACKTRANSFORM, true, st);
   if (overlap) GSCF_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));

@@ -75,6 +75,8 @@ SIGNATURES = {
     "gscf_b200_syev_worksize": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "gscf_b200_syev": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, _LL, _P, _LL, _P, C.c_int, _LL, C.c_int,
                                  _P, C.c_size_t, _P, _P]),
+    "gscf_b200_syevx": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_int, _LL, _P, _LL, _P, C.c_int, _LL, C.c_int,
+                                  _P, C.c_size_t, _P, _P]),
     "gscf_b200_frob_multidot_worksize": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gscf_b200_frob_multidot": (C.c_int, [_P, _P, _LL, _I, C.c_int, C.c_int, C.c_int, C.c_int, _LL, _LL,
                                           C.c_int, _P, C.c_int, _P, C.c_size_t, _P]),

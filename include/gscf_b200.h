@@ -83,6 +83,14 @@ int gscf_b200_syev(int method, int n, double* A, int lda, long long strideA, dou
                    long long stride_w, double* Z, int ldz, long long strideZ, int batch,
                    void* work, size_t work_bytes, int* info_dev, void* stream);
 
+/* Partial spectrum (ScfBaseKeys::n_eigenpairs, ScfBase.hh:87,315-316): all n eigenvalues ascending in w, eigenvectors
+ * only of the n_eigenpairs lowest in the first n_eigenpairs columns of Z (the other columns are unspecified).  The
+ * tridiagonal path skips the eigenvector part of the top-level divide & conquer merge and the back-transformation of
+ * the unwanted vectors; the Jacobi path (n <= 64) computes everything.  Same workspace as gscf_b200_syev. */
+int gscf_b200_syevx(int method, int n, int n_eigenpairs, double* A, int lda, long long strideA, double* w,
+                    long long stride_w, double* Z, int ldz, long long strideZ, int batch, void* work,
+                    size_t work_bytes, int* info_dev, void* stream);
+
 /* out[j] = <E_new, E_j>_F for j < count (E_j = ring + slots[j] * slot_stride), the multi-dot of
  * PulayDiisScf.hh:440-463 reading E_new once.  rows x cols elements per matrix, leading dim ld.
  * batch problems: matrix p at + p * problem_stride, results out[p * out_stride + j]. */

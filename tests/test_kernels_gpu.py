@@ -292,6 +292,47 @@ def test_syev_tridiag_dc(env, n):
     _syev_check(torch, L, L.EIG_TRIDIAG_DC, mats, n)
 
 
+@pytest.mark.parametrize("n,k,batch", [(200, 25, 3), (512, 64, 2), (1024, 128, 1), (130, 129, 2), (300, 1, 2)])
+def test_syevx_partial_spectrum(env, n, k, batch):
+    """gscf_b200_syevx (n_eigenpairs = k < n, ScfBase.hh:87): all eigenvalues, the k lowest eigenvectors - through the
+    partial top-level merge of the divide & conquer.  Random, clustered (heavy deflation: the rank of a root has to count
+    the deflated eigenvalues below it) and nearly diagonal matrices."""
+    torch, L = env
+    rng = np.random.default_rng(n + k)
+    mats = []
+    for b in range(batch):
+        a = rng.standard_normal((n, n))
+        a = a + a.T
+        if b == 1:
+            qm, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            ev = np.repeat(np.arange(1, n // 3 + 2), 3)[:n].astype(float)
+            a = (qm * ev) @ qm.T
+            a = 0.5 * (a + a.T)
+        if b == 2:
+            a = np.diag(np.arange(n, dtype=float)[::-1].copy()) + 1e-9 * a
+        mats.append(a)
+    ld = L.lib.gscf_b200_padded_ld(n)
+    dA = dev(torch, np.concatenate([colmajor(a, ld) for a in mats]))
+    dw = torch.zeros(batch * n, dtype=torch.float64, device="cuda")
+    dZ = torch.zeros(batch * ld * n, dtype=torch.float64, device="cuda")
+    info = torch.full((batch,), 7, dtype=torch.int32, device="cuda")
+    wsz = L.lib.gscf_b200_syev_worksize(n, batch, L.EIG_TRIDIAG_DC)
+    work = torch.zeros(max(1, wsz // 8 + 1), dtype=torch.float64, device="cuda")
+    L.check(L.lib.gscf_b200_syevx(L.EIG_TRIDIAG_DC, n, k, dA.data_ptr(), ld, ld * n, dw.data_ptr(), n, dZ.data_ptr(), ld,
+                                  ld * n, batch, work.data_ptr(), wsz, info.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert info.cpu().numpy().tolist() == [0] * batch
+    w = dw.cpu().numpy().reshape(batch, n)
+    Z = dZ.cpu().numpy().reshape(batch, n, ld)
+    for b, a in enumerate(mats):
+        wref = np.linalg.eigvalsh(a)
+        scale = max(1.0, np.abs(wref).max())
+        z = Z[b][:k, :n].T  # n x k
+        assert np.abs(w[b] - wref).max() < 1e-13 * scale * n
+        assert np.abs(z.T @ z - np.eye(k)).max() < 1e-13 * n
+        assert np.abs(a @ z - z * w[b][:k]).max() < 1e-13 * scale * n
+
+
 def test_syev_tridiag_dc_fock_like(env):
     """The matrices the SCF feeds the solver: X^T F X of the synthetic problem, n = 384."""
     torch, L = env
