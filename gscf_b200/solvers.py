@@ -35,7 +35,11 @@ class GenMap(dict):
 
     def submap(self, prefix: str) -> "GenMap":
         pre = prefix.rstrip("/") + "/"
-        return GenMap({k[len(pre):]: v for k, v in self.items() if k.startswith(pre)})
+        sub = GenMap({k[len(pre):]: v for k, v in self.items() if k.startswith(pre)})
+        nested = self.get(prefix.rstrip("/"))
+        if isinstance(nested, dict):  # a map-valued entry, like krims::GenMap::update(key, GenMap)
+            sub.update(nested)
+        return sub
 
     def update_key(self, key, value):
         if isinstance(value, GenMap):
@@ -473,6 +477,14 @@ class ScfBase:
         self.eigensolver_params = m.submap(ScfBaseKeys.eigensolver_params)
         self.user_eigensolver_tolerance = m.exists("tolerance")
         self.eig_method = m.at("b200/eig_method", self.eig_method)
+        # The "eigensolver" sub-map goes to the inner eigensolver (ScfBase.hh:104, :324): lazyten's key "method" picks
+        # among solvers that return the same eigenpairs; here it picks among this library's dense solvers.  Values lazyten
+        # knows ("auto", "lapack", "arpack") all map to the automatic choice, plus "jacobi" and "tridiag_dc"; its
+        # "tolerance" has no meaning for a direct solver (inner_solver_tolerance is machine epsilon anyway, ScfBase.hh:251).
+        method = self.eigensolver_params.get("method")
+        if isinstance(method, str):
+            self.eig_method = {"jacobi": L.EIG_JACOBI, "tridiag_dc": L.EIG_TRIDIAG_DC, "dc": L.EIG_TRIDIAG_DC}.get(
+                method.lower(), L.EIG_AUTO)
 
     def get_control_params(self, m: GenMap):
         m.update_key(ScfBaseKeys.max_iter, self.max_iter)

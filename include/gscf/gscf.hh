@@ -288,6 +288,16 @@ class ScfBase : public lazyten::IterativeWrapper<lazyten::SolverBase<State>> {
     eigensolver_params = map.submap(ScfBaseKeys::eigensolver_params);
     user_eigensolver_tolerance = map.exists("tolerance");  // top-level lookup, ScfBase.hh:105
     b200_eig_method = map.at("b200/eig_method", b200_eig_method);
+    // The "eigensolver" sub-map goes to the inner eigensolver (ScfBase.hh:104, :324).  lazyten's key "method" picks among
+    // solvers that return the same eigenpairs; here it picks among this library's dense solvers: the values lazyten
+    // knows ("auto", "lapack", "arpack") map to the automatic choice, plus "jacobi" and "tridiag_dc".  Its "tolerance"
+    // has no meaning for a direct solver (inner_solver_tolerance is machine epsilon anyway, ScfBase.hh:251).
+    if (eigensolver_params.exists("method")) {
+      const std::string method = eigensolver_params.at("method", std::string("auto"));
+      if (method == "jacobi") b200_eig_method = GSCF_B200_EIG_JACOBI;
+      else if (method == "tridiag_dc" || method == "dc") b200_eig_method = GSCF_B200_EIG_TRIDIAG_DC;
+      else b200_eig_method = GSCF_B200_EIG_AUTO;
+    }
   }
   void get_control_params(krims::GenMap& map) const {
     base_type::get_control_params(map);

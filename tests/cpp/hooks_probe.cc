@@ -146,6 +146,18 @@ int main() {
   ps.push_new_eigensolution(b, {0, 0});
   matrix_type e1 = pp.residual(ps);
   CHECK(e1.n_rows() == 3 && e1.n_cols() == 2 && e1(1, 0) == -0.25 && e1(2, 1) == -2.0 && e1(0, 0) == 0.0);
+  // ---- the "eigensolver" sub-map reaches the inner eigensolver choice (ScfBase.hh:104) ----
+  {
+    krims::GenMap sub{{"method", std::string("tridiag_dc")}};
+    Diis dsub({{"eigensolver", sub}, {"diis_n_prev_steps", size_t(6)}});
+    CHECK(dsub.b200_eig_method == GSCF_B200_EIG_TRIDIAG_DC && dsub.n_prev_steps == 6);
+    krims::GenMap sub2{{"method", std::string("lapack")}, {"tolerance", 1e-9}};
+    Plain psub({{"eigensolver", sub2}});
+    CHECK(psub.b200_eig_method == GSCF_B200_EIG_AUTO);
+    krims::GenMap back;
+    dsub.get_control_params(back);
+    CHECK(back.submap("eigensolver").at("method", std::string("")) == "tridiag_dc");
+  }
   std::printf(g_fail == 0 ? "PROBE OK\n" : "%d PROBE CHECKS FAILED\n", g_fail);
   return g_fail == 0 ? 0 : 1;
 }

@@ -58,3 +58,19 @@ def test_iteration_recorder_roundtrip(tmp_path):
     z = np.load(str(tmp_path / "t.npz"))
     np.testing.assert_allclose(z["energy_total"], [-12.0, -13.0, -14.0])
     np.testing.assert_allclose(z["orben_2"], [0.0, 1.0, 2.0])
+
+
+def test_eigensolver_submap_selects_the_inner_solver():
+    """ScfBase.hh:104: the "eigensolver" sub-map is handed to the inner eigensolver; its "method" key picks among this
+    library's dense solvers (lazyten's own values all mean the automatic choice), flat and nested spellings alike."""
+    import gscf_b200 as G
+    from gscf_b200 import lib as L
+
+    assert G.PulayDiisScf({"eigensolver": {"method": "jacobi"}}).eig_method == L.EIG_JACOBI
+    assert G.PlainScf({"eigensolver/method": "tridiag_dc"}).eig_method == L.EIG_TRIDIAG_DC
+    s = G.TruncatedOptDampScf({"eigensolver": G.GenMap({"method": "arpack", "tolerance": 1e-9})})
+    assert s.eig_method == L.EIG_AUTO and s.eigensolver_params["tolerance"] == 1e-9
+    assert G.PlainScf({}).eig_method == L.EIG_AUTO
+    m = G.GenMap()
+    G.PulayDiisScf({"eigensolver": {"method": "jacobi"}}).get_control_params(m)
+    assert m["eigensolver/method"] == "jacobi"
