@@ -18,7 +18,11 @@
 namespace gscfb {
 namespace {
 
-constexpr int TFB_PW = 32;
+#ifndef GSCF_TFB_PW
+#define GSCF_TFB_PW 32
+#endif
+constexpr int TFB_PW = GSCF_TFB_PW;  // pending reflectors between two boundary sweeps (<= 32: workspace and lane mappings)
+static_assert(TFB_PW >= 4 && TFB_PW <= 32, "TFB_PW");
 
 struct TfbArgs {
   TfArgs b;

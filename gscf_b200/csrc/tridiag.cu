@@ -714,7 +714,7 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
     if (T == 512) return tf_launch<8, false, 512>(a, G, cnt, cluster, smem, st);
     return tf_launch<8, false, 1024>(a, G, cnt, cluster, smem, st);
   };
-  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW == 32 && n > tf_unblocked_below() &&
+  const bool use_blocked = blocked && !smem_a && !cluster && G <= 256 && TFB_PW <= 32 && n > tf_unblocked_below() &&
                            ceil_div(n, G) <= TF_MAXS && (jstop == 0 || n - jstop < tf_unblocked_below());
   if (cluster && smem_a) {
     int mc = T == 128 ? tf_max_clusters<8, true, 128>(G, smem) : K <= 2 ? tf_max_clusters<2, true, 256>(G, smem)
