@@ -750,13 +750,18 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
 // Returns -1 when the fused kernels do not cover the case (caller falls back to the panel kernels).
 int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& ws, int batch, const int* map,
                          cudaStream_t st) {
-  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144, handover_on = 1, t_smem = 1664, solo_split = 1;
+  static int enabled = -1, phases_on = 0, t_cluster = 592, t_solo = 144, handover_on = 1, t_smem = 1664, solo_split = 1,
+             solo_tail = 1;
   if (enabled < 0) {
     const char* sse = getenv("GSCF_B200_TF_SOLO_SPLIT");
     solo_split = (sse && sse[0] == '0') ? 0 : 1;
     { const char* sr = getenv("GSCF_B200_TF_SOLO_REG"); if (sr && sr[0] == '0') solo_split = 0; }
     { const char* so = getenv("GSCF_B200_TF_SOLO"); if (so && so[0] == '0') solo_split = 0; }
     { const char* fg = getenv("GSCF_B200_TF_GLOBAL"); if (fg && fg[0] == '1') solo_split = 0; }
+    // one or two large matrices: the last 128 columns leave the all-SM kernel (3.5 us per column: its floor is the L2
+    // exchange between 148 CTAs) for the single-CTA register kernels (no exchange: ~1.7 and 0.7 us per column)
+    const char* ste = getenv("GSCF_B200_TF_SOLO_TAIL");
+    solo_tail = (ste && ste[0] == '0') ? 0 : solo_split;
     const char* env = getenv("GSCF_B200_TRD_FUSED");
     enabled = (env && env[0] == '0') ? 0 : 1;
     int dev = 0, coop = 0, sms = 0;
@@ -786,7 +791,8 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     // a single matrix too large for shared memory: once the trailing block fits (order t_smem on all SMs) hand it to the
     // shared-memory kernel - its sweeps cost half of the L2 ones and its O(n) part handles fewer rows per thread
     if (handover_on && batch == 1 && phase == 0 && ns > t_smem + 128) jstop = (ns - t_smem) & ~1;
-    else if (solo_split && phase == 0 && ns > 96 && ns <= 128) jstop = (ns - 64) & ~1;  // register kernel: 128-row -> 64-row layout
+    else if (solo_split && ns > 96 && ns <= 128) jstop = (ns - 64) & ~1;  // register kernel: 128-row -> 64-row layout
+    else if (solo_tail && batch <= 2 && ns > 192 && ns <= 2048) jstop = (ns - 128) & ~1;  // tail of a large matrix -> one CTA
     else if (phases_on && ns <= tf_unblocked_below() && ns <= 2048 && phase < 2) {
       if (t_cluster > t_solo && ns > t_cluster + 64 && batch <= 8) jstop = ns - t_cluster;
       else if (t_solo > 0 && ns > t_solo + 32) jstop = ns - t_solo;
@@ -794,7 +800,8 @@ int tridiagonalise_fused(int n, double* A, int lda, long long sA, const TrdWs& w
     }
     const bool prefer_cluster = phases_on && phase > 0 && batch <= 8 && ns <= t_cluster + 64;
     // counters: phase 0 uses [0, 2 cap) (y exchange + the blocked kernel's partial dots), phases 1, 2 one array each
-    unsigned* counters = phase == 0 ? ws.bar : ws.bar + (size_t)(phase + 1) * ws.cap;
+    // (the single-CTA kernels of later phases use no counters)
+    unsigned* counters = phase == 0 ? ws.bar : ws.bar + (size_t)std::min(phase + 1, 3) * ws.cap;
     const int rc = tf_phase(ns, n, A + (size_t)off * lda + off, lda, sA, ws, ws.d + off, ws.e + off, ws.tau + off, counters,
                             batch, map, jstop, prefer_cluster, st);
     if (rc != GSCF_B200_OK) {
