@@ -42,7 +42,7 @@ struct TrdWs {
   double* VW;           // [cap][ld * 4*NB]  [V|W] and [W|V] panels for the fused rank-2k update
   unsigned long long* amax;  // [cap] max |a_ij| (bit pattern)
   double* ascale;       // [cap] 1, or the norm an extreme matrix was divided by
-  double* SK;           // split-k partials: min(cap,16) * 16 * NBQ * n
+  double* SK;           // split-k partials: min(cap,16) * 16 * 2 NBQ * n
   double* X;            // [cap][4 np] exchange slots of the fused tridiagonalisation (trd_fused.cuh)
   double* VPW;          // [cap][2][32][np] pending reflector panels of the blocked fused kernel
   double* PQ;           // [cap][2][256][64] partial dots of the blocked fused kernel
@@ -55,7 +55,7 @@ struct TrdWs {
   int nbq;              // blocks of nbw reflectors
   int nbw;              // block width of the back-transformation: 64 for n <= 256 (batches: small T factors, several
                         // CTAs per SM in larft), NBQ = 128 above
-  double* Yw;           // [cap][NBQ*n]
+  double* Yw;           // [cap][2 NBQ * n]  (a merged pair of blocks: 2 NBQ rows)
   int n, ld, nrb, ncb, cap;
 };
 inline int ws_cap_hint(const TrdWs& ws) { return ws.cap; }
@@ -407,7 +407,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.VPW = cv.take<double>((size_t)cap * 2 * 32 * round_up(n, 2));
   ws.PQ = cv.take<double>((size_t)cap * 2 * 256 * 64);
   ws.VW = cv.take<double>((size_t)cap * ld * 4 * NB);
-  ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * NBQ * n);
+  ws.SK = cv.take<double>((size_t)std::min(cap, 16) * 16 * 2 * NBQ * n);
   ws.amax = cv.take<unsigned long long>((size_t)cap);
   ws.ascale = cv.take<double>((size_t)cap);
   ws.X = cv.take<double>((size_t)cap * tf_x_doubles(n));
@@ -420,7 +420,7 @@ void carve_trd(Carver& cv, int n, int cap, TrdWs& ws) {
   ws.Gall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
   ws.Tall = cv.take<double>((size_t)cap * ws.nbq * NBQ * NBQ);
   ws.bdesc = cv.take<GemmDesc>((size_t)cap * ws.nbq);
-  ws.Yw = cv.take<double>((size_t)cap * NBQ * n);
+  ws.Yw = cv.take<double>((size_t)cap * 2 * NBQ * n);
 }
 
 int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, int j0, int pw, int batch,
@@ -868,6 +868,46 @@ __global__ void bt_desc_kernel(TrdWs ws, int which, int batch, const int* __rest
   ws.bdesc[idx] = d;
 }
 
+// Merging two consecutive block reflectors into one of twice the width (k = 256 instead of 128 in the Z-dependent GEMMs,
+// half as many of them):  (I - W0 V0^T)(I - W1 V1^T) = I - [W0 | W1 - W0 (V0^T W1)] [V0 | V1]^T.
+// which = 2:  M = V0(j1+1:, :)^T W1           (nbw x pw1, into the G slot of block b0 - larft is done with it)
+// which = 3:  W1' = W1 - W0 M, two descriptors per pair: rows j0+1 .. j1 (W1 is zero there: beta = 0) and rows j1+1 ..
+__global__ void bt_pair_desc_kernel(TrdWs ws, int which, int batch, int npairs, const int* __restrict__ map) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * npairs) return;
+  const int z = idx / npairs, p = idx - z * npairs;
+  const long long q = map ? map[z] : z;
+  const int n = ws.n, nbw = ws.nbw, b0 = 2 * p, j0 = b0 * nbw, j1 = j0 + nbw;
+  const int pw1 = min(nbw, n - 1 - j1), m1 = n - j1 - 1;
+  double* Vq = ws.Vf + q * (long long)ws.ld * n;
+  double* Wq = ws.Wf + q * (long long)ws.ld * n;
+  double* M = ws.Gall + (q * ws.nbq + b0) * NBQ * NBQ;
+  if (which == 2) {
+    GemmDesc d;
+    d.A = Vq + (size_t)j0 * ws.ld + j1 + 1; d.lda = ws.ld;
+    d.B = Wq + (size_t)j1 * ws.ld + j1 + 1; d.ldb = ws.ld;
+    d.C = M; d.ldc = nbw;
+    d.m = nbw; d.n = pw1; d.k = m1; d.alpha = 1.0; d.beta = 0.0;
+    ws.bdesc[idx] = d;
+  } else {
+    GemmDesc top, bot;
+    top.A = Wq + (size_t)j0 * ws.ld + j0 + 1; top.lda = ws.ld; top.B = M; top.ldb = nbw;
+    top.C = Wq + (size_t)j1 * ws.ld + j0 + 1; top.ldc = ws.ld;
+    top.m = nbw; top.n = pw1; top.k = nbw; top.alpha = -1.0; top.beta = 0.0;
+    bot.A = Wq + (size_t)j0 * ws.ld + j1 + 1; bot.lda = ws.ld; bot.B = M; bot.ldb = nbw;
+    bot.C = Wq + (size_t)j1 * ws.ld + j1 + 1; bot.ldc = ws.ld;
+    bot.m = m1; bot.n = pw1; bot.k = nbw; bot.alpha = -1.0; bot.beta = 1.0;
+    ws.bdesc[2 * idx] = top;
+    ws.bdesc[2 * idx + 1] = bot;
+  }
+}
+
+bool bt_pairing() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GSCF_B200_BT_PAIR"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 // Z <- Q Z with the reflectors stored in A / tau:  Q = H(0) .. H(n-2) = prod_b (I - V_b T_b V_b^T).
 // Everything that does not depend on Z is done up front for all blocks at once (V, G_b, T_b, W_b = V_b T_b: four
 // launches); the sequential part is two GEMMs per block:  Y = V_b^T Z,  Z -= W_b Y.
@@ -895,6 +935,21 @@ int back_transform_setup(int n, const double* A, int lda, long long sA, const Tr
     gp.descs = ws.bdesc; gp.kbatch = 1; gp.ksplit = 1;
     GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, ws.nbw, st));
   }
+  const int npairs = nblocks / 2;
+  if (bt_pairing() && npairs > 0) {
+    bt_pair_desc_kernel<<<ceil_div(batch * npairs, 128), 128, 0, st>>>(ws, 2, batch, npairs, map);
+    count_launch();
+    GSCF_CHECK_LAUNCH();
+    GemmParams gm{};
+    gm.descs = ws.bdesc; gm.kbatch = 1; gm.ksplit = 1;
+    GSCF_TRY(launch_gemm(true, false, gm, batch * npairs, ws.nbw, ws.nbw, st));
+    bt_pair_desc_kernel<<<ceil_div(batch * npairs, 128), 128, 0, st>>>(ws, 3, batch, npairs, map);
+    count_launch();
+    GSCF_CHECK_LAUNCH();
+    GemmParams gw{};
+    gw.descs = ws.bdesc; gw.kbatch = 1; gw.ksplit = 1;
+    GSCF_TRY(launch_gemm(false, false, gw, batch * npairs * 2, n, ws.nbw, st));
+  }
   return GSCF_B200_OK;
 }
 
@@ -904,21 +959,37 @@ int back_transform(int n, const TrdWs& ws, double* Z, int ldz, long long sZ, int
   const int nz = (nvec > 0 && nvec < n) ? nvec : n;  // columns of Z that are wanted
   const int nref = n - 1;  // reflectors 0..n-2
   const int nblocks = ws.nbq;
-  for (int b = nblocks - 1; b >= 0; --b) {
-    const int j0 = b * ws.nbw;
-    const int pw = std::min(ws.nbw, nref - j0);
+  constexpr int LDY = 2 * NBQ;
+  // one (merged) block reflector: pw reflectors starting at column j0
+  auto apply = [&](int j0, int pw) -> int {
     const int m = n - j0 - 1;  // rows j0+1 .. n-1
     const double* Vb = ws.Vf + (size_t)j0 * ws.ld + j0 + 1;
     const double* Wb = ws.Wf + (size_t)j0 * ws.ld + j0 + 1;
-    // Y = V_b^T Z(j0+1:, :)   (pw x n, ld NBQ)
-    GemmParams y = gemm_params(pw, nz, m, 1.0, Vb, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, NBQ);
-    y.sA = (long long)ws.ld * n; y.sB = sZ; y.sC = (long long)NBQ * n; y.batch_map = map;
+    // Y = V_b^T Z(j0+1:, :)   (pw x nz, ld LDY)
+    GemmParams y = gemm_params(pw, nz, m, 1.0, Vb, ws.ld, Z + j0 + 1, ldz, 0.0, ws.Yw, LDY);
+    y.sA = (long long)ws.ld * n; y.sB = sZ; y.sC = (long long)LDY * n; y.batch_map = map;
     const int splits = batch >= 16 ? 1 : std::max(1, std::min(8, m / 128));  // long-k TN product: split-k
     GSCF_TRY(launch_gemm_splitk(true, false, y, batch, splits, ws.SK, st));
     // Z(j0+1:, :) -= W_b Y
-    GemmParams u = gemm_params(m, nz, pw, -1.0, Wb, ws.ld, ws.Yw, NBQ, 1.0, Z + j0 + 1, ldz);
-    u.sA = (long long)ws.ld * n; u.sB = (long long)NBQ * n; u.sC = sZ; u.batch_map = map;
-    GSCF_TRY(launch_gemm(false, false, u, batch, m, nz, st));
+    GemmParams u = gemm_params(m, nz, pw, -1.0, Wb, ws.ld, ws.Yw, LDY, 1.0, Z + j0 + 1, ldz);
+    u.sA = (long long)ws.ld * n; u.sB = (long long)LDY * n; u.sC = sZ; u.batch_map = map;
+    return launch_gemm(false, false, u, batch, m, nz, st);
+  };
+  if (bt_pairing() && nblocks >= 2) {
+    // blocks (2p, 2p+1) were merged by the set-up; an odd last block stands alone
+    if (nblocks & 1) {
+      const int j0 = (nblocks - 1) * ws.nbw;
+      GSCF_TRY(apply(j0, std::min(ws.nbw, nref - j0)));
+    }
+    for (int p = nblocks / 2 - 1; p >= 0; --p) {
+      const int j0 = 2 * p * ws.nbw, j1 = j0 + ws.nbw;
+      GSCF_TRY(apply(j0, ws.nbw + std::min(ws.nbw, nref - j1)));
+    }
+  } else {
+    for (int b = nblocks - 1; b >= 0; --b) {
+      const int j0 = b * ws.nbw;
+      GSCF_TRY(apply(j0, std::min(ws.nbw, nref - j0)));
+    }
   }
   return GSCF_B200_OK;
 }

@@ -395,6 +395,9 @@ def test_syev_special_matrices(env, n):
     (1000, 20, {}),                                                                 # SYMH, four rows per thread
     (512, 16, {"GSCF_B200_TF_SYMH": "0"}),                                          # clusters of 4 in L2, full-column sweep
     (1024, 2, {"GSCF_B200_TRD_FUSED": "0"}),                                        # three-kernels-per-column fall-back
+    (1024, 1, {"GSCF_B200_BT_PAIR": "0"}),                                          # back-transformation block by block (no merged pairs)
+    (700, 3, {"GSCF_B200_BT_PAIR": "0"}),
+    (385, 2, {}),                                                                   # three blocks: one merged pair + a single block
     (1024, 1, {"GSCF_B200_TF_SOLO_TAIL": "0"}),                                     # all-SM register kernel to the last column
     (1024, 2, {}),                                                                  # two matrices: tail of each in one CTA
     (2048, 1, {}),                                                                  # L2 kernel, hand-over to shared memory, then to one CTA
