@@ -902,10 +902,13 @@ __global__ void bt_pair_desc_kernel(TrdWs ws, int which, int batch, int npairs, 
   }
 }
 
-bool bt_pairing() {
+// Measured (B200): one matrix of order 1024 back-transformation 0.47 -> 0.32 ms, order 4096 11.5 -> 9.5 ms; batches are
+// in the throughput regime, where the wider blocks gain nothing (4096 x 128: 29.7 -> 27.5 ms but the longer set-up slows
+// the concurrent D&C stage by as much) or lose (512 x 512: 154.6 -> 173.8 ms): pairs only for fewer than 16 matrices.
+bool bt_pairing(int batch) {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("GSCF_B200_BT_PAIR"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on != 0;
+  if (on < 0) { const char* e = getenv("GSCF_B200_BT_PAIR"); on = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }
+  return on == 2 || (on == 1 && batch < 16);
 }
 
 // Z <- Q Z with the reflectors stored in A / tau:  Q = H(0) .. H(n-2) = prod_b (I - V_b T_b V_b^T).
@@ -936,7 +939,7 @@ int back_transform_setup(int n, const double* A, int lda, long long sA, const Tr
     GSCF_TRY(launch_gemm(false, false, gp, batch * nblocks, n, ws.nbw, st));
   }
   const int npairs = nblocks / 2;
-  if (bt_pairing() && npairs > 0) {
+  if (bt_pairing(batch) && npairs > 0) {
     bt_pair_desc_kernel<<<ceil_div(batch * npairs, 128), 128, 0, st>>>(ws, 2, batch, npairs, map);
     count_launch();
     GSCF_CHECK_LAUNCH();
@@ -975,7 +978,7 @@ int back_transform(int n, const TrdWs& ws, double* Z, int ldz, long long sZ, int
     u.sA = (long long)ws.ld * n; u.sB = (long long)LDY * n; u.sC = sZ; u.batch_map = map;
     return launch_gemm(false, false, u, batch, m, nz, st);
   };
-  if (bt_pairing() && nblocks >= 2) {
+  if (bt_pairing(batch) && nblocks >= 2) {
     // blocks (2p, 2p+1) were merged by the set-up; an odd last block stands alone
     if (nblocks & 1) {
       const int j0 = (nblocks - 1) * ws.nbw;
