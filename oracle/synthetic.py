@@ -59,8 +59,13 @@ class SyntheticDFProblem:
     """Fock-like plugin (``FocklikeMatrix_i``) for the synthetic DF problem."""
 
     def __init__(self, n_bas: int, n_alpha: int, n_beta: int | None = None, n_aux: int | None = None,
-                 seed: int = 0, g: float = 1.0, unrestricted: bool | None = None):
+                 seed: int = 0, g: float = 1.0, unrestricted: bool | None = None, summation: str = "pairwise"):
         n = n_bas
+        # how the energy traces are summed: numpy's pairwise reduction (default) or a plain left-to-right sum.  Both are
+        # legitimate fp64 evaluations of the same formula; the second exists to show how far the damped TODA branch moves
+        # under a mere change of summation order (tests/test_toda_sensitivity_cpu.py)
+        assert summation in ("pairwise", "sequential")
+        self._sum = (lambda a: float(np.sum(a))) if summation == "pairwise" else (lambda a: float(np.cumsum(a.ravel())[-1]))
         self.n_bas = n
         self.n_alpha = n_alpha
         self.n_beta = n_alpha if n_beta is None else n_beta
@@ -95,8 +100,8 @@ class SyntheticDFProblem:
             J = np.tensordot(gamma, B, 1)
             K = _k_from_y(Y)
             F = H + J - K
-            e1 = 2.0 * float(np.sum(H * D))
-            e2 = float(np.sum(J * D)) - float(np.sum(K * D))
+            e1 = 2.0 * self._sum(H * D)
+            e2 = self._sum(J * D) - self._sum(K * D)
             return F[None], e1, e2
         ca = C[0][:, : self.n_alpha]
         cb = C[1 if C.shape[0] > 1 else 0][:, : self.n_beta]
@@ -107,6 +112,6 @@ class SyntheticDFProblem:
         Ka = _k_from_y(Ya)
         Kb = _k_from_y(Yb)
         Dt = Da + Db
-        e1 = float(np.sum(H * Dt))
-        e2 = 0.5 * (float(np.sum(J * Dt)) - float(np.sum(Ka * Da)) - float(np.sum(Kb * Db)))
+        e1 = self._sum(H * Dt)
+        e2 = 0.5 * (self._sum(J * Dt) - self._sum(Ka * Da) - self._sum(Kb * Db))
         return np.stack([H + J - Ka, H + J - Kb]), e1, e2
