@@ -479,6 +479,10 @@ def measure(job, w, steps, warmup, cpu_baseline=True, sample_clocks=False, probl
                             "exchange_floor_source": "scripts/micro/exchange.cu on B200: ~4 dependent L2 round trips "
                                                      "(3600 cycles for 148 CTAs with fence + atomic + poll)",
                             "sm_mhz": sm_mhz, "matrices_in_flight": mats_in_flight}}
+            if 192 < n <= 1664 + 128 and P_local * nblk <= 2:
+                roofline["launch_note"] = ("one 'launch' = one tridiagonalisation = three kernels: the all-SM register / "
+                                           "shared-memory kernel down to trailing order 128, then the single-CTA register "
+                                           "kernels (128-row and 64-row layouts); cycles_per_column averages over all of them")
             if n > 1664 + 128 and P_local * nblk == 1:
                 roofline["launch_note"] = ("one 'launch' = one tridiagonalisation = two kernels: the L2/HBM kernel down "
                                            "to trailing order 1664, then the shared-memory kernel (hand-over); "
