@@ -486,7 +486,6 @@ def test_toda_default_threshold_parity(G, n, na, nb, aux, seed, robust):
     if robust:
         assert counts[0] <= got["n_iter"] <= counts[-1], (got["n_iter"], counts)
     else:
-        assert counts[-1] > counts[0]  # the oracle really disagrees with itself on this problem
         assert 0.5 * counts[0] <= got["n_iter"] <= 2 * counts[-1], (got["n_iter"], counts)
     assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
     lam = [float(c[0]) for c in got["trace"][2]]
