@@ -365,6 +365,25 @@ def test_c2_full_size_parity(G):
     assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < TOL_D
 
 
+def test_c2_size_toda_parity(G):
+    """TruncatedOptDampScf at the size of BASELINE configs[1] (n_bf = 1024, n_occ = 128, n_aux = 64) through the production
+    eigensolver: the damped branch (lambda = 1, 0.377, 1, 0.267, 0.806, ...) and the keep / flip rule
+    (TruncatedOptDampScf.hh:273-277, :349-409) against the oracle - iteration count at 1e-5 (the threshold up to which the
+    algorithm is reproducible, tests/test_toda_sensitivity_cpu.py), energy to 1e-10, every damping coefficient."""
+    n, o, aux = 1024, 128, 64
+    got = _run_synthetic(G, n, o, aux, "toda", params={"max_error_norm": 1e-5})
+    ref, p = _oracle_synthetic(n, o, aux, "toda", max_error_norm=1e-5)
+    assert got["n_iter"] == ref.n_iter
+    assert abs(got["e"][0][0] + got["e"][1][0] - ref.energy_total) < TOL_E
+    lam = [float(c[0]) for c in got["trace"][2]]
+    assert min(lam) < 0.5
+    np.testing.assert_allclose(lam, ref.trace_coeff, rtol=2e-3, atol=1e-8)
+    np.testing.assert_allclose(lam[:8], ref.trace_coeff[:8], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(got["trace"][1], ref.trace_error, rtol=2e-3, atol=1e-12)
+    assert np.abs(got["w"][0] - ref.orben[0]).max() < 1e-6
+    assert np.linalg.norm(got["D"][0] - ref.density(o, o)[0]) < 1e-5
+
+
 def test_c3_full_size_parity(G):
     """BASELINE configs[2] at full size (n_bf = 4096, n_occ = 512, n_aux = 64 as in bench.py, DIIS 10) against the ORACLE:
     the north_star gate through the blocked / hand-over tridiagonalisation kernels - same iteration count, |dE| <= 1e-10,
