@@ -117,15 +117,10 @@ constexpr int TF_RROWS = 1024;  // rows covered by the register variant: row pai
 //   y_r += A(r, c) v_c   (row part: accumulated in the registers of the thread that owns row r - no reduction - and
 //                         published as one n-vector per CTA; every CTA adds the G vectors after the SAME exchange).
 // The stale upper triangle is never read as data.
-// PF (with SYMH, one row pair per thread): the loads of the NEXT group of eight columns are issued before the current group
-// is processed - a CTA that has the SM to itself (few matrices: the 8-GPU share of C5) otherwise walks its column groups
-// as a chain of dependent L2 round trips.
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1,
-          bool PF = false>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1>
 __global__ void __launch_bounds__(T, MINB)
 trd_fused_kernel(const TfArgs a) {
   static_assert(!SYMH || (!SMEM_A && !SOLO && !REGA), "SYMH is a variant of the global-memory sweep");
-  static_assert(!PF || (SYMH && KMAX <= 2), "the prefetching sweep is written for one row pair per thread");
   const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = T / 32;
   const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
@@ -209,82 +204,7 @@ trd_fused_kernel(const TfArgs a) {
       double* Xy = X + (size_t)(j & 1) * xhalf;
       double* Xr = Xy + np;
       const bool pub_raw = (g + s0 * G == first);  // I own column j+1: its updated values are the raw column
-      if (SYMH && PF) {
-        // one row pair per thread: rows r, r + 1 of every owned column; v_{j-1}, w_{j-1}, v_j at these rows once per step
-        const int p = tid;
-        const bool prow = p < npairs;
-        const int r = r_lo + 2 * p;
-        double2 vp = make_double2(0.0, 0.0), wp = vp, vn = vp;
-        if (prow) {
-          vp = *reinterpret_cast<const double2*>(svn + r);
-          wp = *reinterpret_cast<const double2*>(sw + r);
-          vn = *reinterpret_cast<const double2*>(svc + r);
-        }
-        const bool odd_tail = (r + 1 >= n);
-        double2 rowacc = make_double2(0.0, 0.0);
-        double2 av[TF_CG], avn[TF_CG];
-        // a group's loads: only the columns whose diagonal is at or above row r + 1 (lower triangle)
-        auto issue = [&](int sg, double2* dst) {
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) {
-            const int c = g + (sg + u) * G;
-            dst[u] = make_double2(0.0, 0.0);
-            if (prow && sg + u < S && r + 1 >= c) dst[u] = *reinterpret_cast<const double2*>(A + (size_t)c * lda + r);
-          }
-        };
-        if (s0 < S) issue(s0, av);
-        for (int sg = s0; sg < S; sg += TF_CG) {
-          if (sg + TF_CG < S) issue(sg + TF_CG, avn);
-          double acc[TF_CG];
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) {
-            const int slot = sg + u;
-            const int c = g + slot * G;
-            acc[u] = 0.0;
-            if (prow && slot < S && r + 1 >= c) {
-              const double wcu = sw[c], vcu = svn[c], vjcu = svc[c];  // w_{j-1}(c), v_{j-1}(c), v_j(c)
-              double* col = A + (size_t)c * lda;
-              double2 x = av[u];
-              x.x = fma(-vp.x, wcu, fma(-wp.x, vcu, x.x));
-              x.y = fma(-vp.y, wcu, fma(-wp.y, vcu, x.y));
-              if (odd_tail) {
-                x.y = 0.0;
-                col[r] = x.x;
-              } else {
-                *reinterpret_cast<double2*>(col + r) = x;
-              }
-              if (pub_raw && slot == s0) *reinterpret_cast<double2*>(Xr + r) = x;
-              acc[u] = fma(r >= c ? x.x : 0.0, vn.x, x.y * vn.y);
-              rowacc.x = fma(r > c ? x.x : 0.0, vjcu, rowacc.x);
-              rowacc.y = fma(r + 1 > c ? x.y : 0.0, vjcu, rowacc.y);
-            }
-          }
-          {
-            static_assert(TF_CG == 8, "butterfly below is written for 8 accumulators");
-            const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-            double a4[4], a2[2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
-              a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
-              a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-            if ((lane & 3) == 0 && sg + u < S) spart[warp * smax + sg + u] = a1;
-          }
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) av[u] = avn[u];
-        }
-        double* Xrow = Xy + (size_t)(2 + g) * np;
-        if (prow) tf_st2(Xrow + r, rowacc.x, rowacc.y);
-      } else if (SYMH) {
+      if (SYMH) {
         constexpr int KP = (KMAX + 1) / 2;  // row pairs per thread
         double2 rowacc[KP];
 #pragma unroll

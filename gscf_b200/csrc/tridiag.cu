@@ -509,10 +509,9 @@ int trailing_update(int n, double* A, int lda, long long sA, const TrdWs& ws, in
 }
 
 // ---- fused one-launch tridiagonalisation (trd_fused.cuh) ---------------------------------------------------
-template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1,
-          bool PF = false>
+template <int KMAX, bool SMEM_A, int T, bool SOLO = false, bool REGA = false, bool SYMH = false, int MINB = 1>
 int tf_launch(const TfArgs& a, int G, int cnt, bool cluster, size_t smem, cudaStream_t st) {
-  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA, SYMH, MINB, PF>;
+  auto kern = trd_fused_kernel<KMAX, SMEM_A, T, SOLO, REGA, SYMH, MINB>;
   // function attributes are per device (and this library may drive several GPUs / host threads from one process):
   // set them on the current device before every launch - two cheap host calls per tridiagonalisation
   GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -632,17 +631,12 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
   // measured (128 matrices of order 512, whole eigensolve): 16-CTA clusters in shared memory 43.6 ms, clusters of 4
   // working in L2 39.5 ms (37 matrices in flight instead of 8)
   if (batch_global < 0) { const char* bg = getenv("GSCF_B200_TF_BATCH_GLOBAL"); batch_global = bg ? atoi(bg) : 4; }
-  static int pf_on = -1;
-  if (pf_on < 0) { const char* pe = getenv("GSCF_B200_TF_SYMH_PF"); pf_on = (pe && pe[0] == '0') ? 0 : 1; }
-  bool symh_pf = false;
   if (solo) {
     G = 1; smem_a = true;
   } else if (batch_global > 0 && batch * g_smem > sms && g_smem > batch_global && n <= 2048) {
     // many matrices, each too large for the shared memory of a few CTAs: small clusters working in L2, more in flight
     G = batch_global;
     cluster = true; smem_a = false;
-    // ... but few enough that clusters of 2 give every CTA its own SM: prefetching symmetric-half sweep (n <= 512)
-    if (pf_on && n <= 512 && batch * 2 <= sms && jstop == 0) { G = 2; symh_pf = true; }
   } else if (g_smem > 0 && g_smem <= 16 && (prefer_cluster || batch * g_smem > sms)) {
     // one thread-block cluster per matrix, scheduled by the hardware: batches that do not fit side by side, and the
     // middle phase of a single reduction (the cluster barrier is cheaper than the L2 counter exchange)
@@ -704,8 +698,6 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
       // (the full-column sweep: 61.5 ms); GSCF_B200_TF_SYMH_OCC=1 selects the one-CTA-per-SM build
       static int occ2 = -1;
       if (occ2 < 0) { const char* oe = getenv("GSCF_B200_TF_SYMH_OCC"); occ2 = (oe && oe[0] == '1') ? 0 : 1; }
-      // few matrices (their clusters of 2 leave every CTA an SM of its own): the prefetching sweep, full register budget
-      if (symh_pf && K <= 2) return tf_launch<2, false, 256, false, false, true, 1, true>(a, G, cnt, cluster, smem, st);
       if (occ2 && K <= 2) return tf_launch<2, false, 256, false, false, true, 2>(a, G, cnt, cluster, smem, st);
       if (occ2 && K <= 4) return tf_launch<4, false, 256, false, false, true, 2>(a, G, cnt, cluster, smem, st);
       if (K <= 2) return tf_launch<2, false, 256, false, false, true>(a, G, cnt, cluster, smem, st);

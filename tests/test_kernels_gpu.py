@@ -387,10 +387,9 @@ def test_syev_special_matrices(env, n):
     (257, 9, {"GSCF_B200_DC_SECULAR": "thread", "GSCF_B200_DC_LEAF": "32"}),
     (128, 40, {"GSCF_B200_DC_LEAF": "32"}),                                         # D&C leaves of 32 (the default above 1024 matrices)
     (128, 4, {"GSCF_B200_TF_SOLO_REG": "0"}),                                       # n <= 128 through the shared-memory SOLO
-    (512, 16, {}),                                                                  # few matrices: clusters of 2 in L2, lower triangle only, prefetching sweep
+    (512, 16, {}),                                                                  # clusters of 4 in L2, lower triangle only (SYMH)
     (512, 16, {"GSCF_B200_TF_CLUSTER_BARRIER": "0"}),                               # SYMH with the L2 counter exchange
-    (512, 16, {"GSCF_B200_TF_SYMH_PF": "0"}),                                       # SYMH without the prefetching sweep (clusters of 4, two CTAs per SM)
-    (512, 16, {"GSCF_B200_TF_SYMH_PF": "0", "GSCF_B200_TF_SYMH_OCC": "1"}),         # SYMH, one CTA per SM build
+    (512, 16, {"GSCF_B200_TF_SYMH_OCC": "1"}),                                      # SYMH, one CTA per SM build
     (512, 20, {"GSCF_B200_TF_BATCH_GLOBAL": "2"}),                                  # SYMH, clusters of 2
     (401, 30, {}),                                                                  # SYMH, odd order
     (1000, 20, {}),                                                                 # SYMH, four rows per thread
