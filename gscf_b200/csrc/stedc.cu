@@ -541,7 +541,7 @@ dc_select_kernel(StedcWs ws, int lev_out, int nvec, const int* __restrict__ map)
 // output, and write the two GEMM descriptors of this merge.
 __global__ void __launch_bounds__(128)
 dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin, int ldin, long long sin,
-                 double* __restrict__ Zout, int ldout, long long sout, int nodes, int partial,
+                 double* __restrict__ Zout, int ldout, long long sout, int nodes, int partial, int cpb,
                  const int* __restrict__ map) {
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
@@ -568,21 +568,29 @@ dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin,
     dsc[0] = top;
     dsc[1] = bot;
   }
-  const int c = blockIdx.x;
-  if (c >= k) return;
-  if (c < K) {
-    const int src = (ws.ndcol + q * n + lo)[c];
-    const int dst = (ws.gpos + q * n + lo)[c];
-    const double* x = Zq + (size_t)(lo + src) * ldin + lo;
-    double* y = Gq + (size_t)dst * ws.ld;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = x[i];
-  } else {
-    const int tdx = c - K;
-    const int src = (ws.dcol + q * n + lo)[tdx];
-    const double* x = Zq + (size_t)(lo + src) * ldin + lo;
-    double* y = Zo + (size_t)(lo + c) * ldout + lo;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = x[i];
-    if (threadIdx.x == 0) (ws.lam[lev_out] + q * n + lo)[c] = (ws.dwork + q * n + lo)[src];
+  // cpb == 1: one column per block (large merges: the whole block streams one long column); cpb > 1: one column per
+  // WARP, cpb columns per block - with short columns (batches of small merges) a block per column was bound by the
+  // block scheduling rate (4096 x 129 blocks of 1 KB each: 0.35 - 0.4 ms per launch at n = 128)
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c_begin = cpb == 1 ? blockIdx.x : blockIdx.x * cpb + warp;
+  const int c_end = cpb == 1 ? blockIdx.x + 1 : min(k, (int)(blockIdx.x + 1) * cpb);
+  const int c_step = cpb == 1 ? 1 : nwarp;
+  const int i0 = cpb == 1 ? threadIdx.x : lane, istep = cpb == 1 ? blockDim.x : 32;
+  for (int c = c_begin; c < c_end && c < k; c += c_step) {
+    if (c < K) {
+      const int src = (ws.ndcol + q * n + lo)[c];
+      const int dst = (ws.gpos + q * n + lo)[c];
+      const double* x = Zq + (size_t)(lo + src) * ldin + lo;
+      double* y = Gq + (size_t)dst * ws.ld;
+      for (int i = i0; i < k; i += istep) y[i] = x[i];
+    } else {
+      const int tdx = c - K;
+      const int src = (ws.dcol + q * n + lo)[tdx];
+      const double* x = Zq + (size_t)(lo + src) * ldin + lo;
+      double* y = Zo + (size_t)(lo + c) * ldout + lo;
+      for (int i = i0; i < k; i += istep) y[i] = x[i];
+      if (i0 == 0) (ws.lam[lev_out] + q * n + lo)[c] = (ws.dwork + q * n + lo)[src];
+    }
   }
 }
 
@@ -606,19 +614,27 @@ __global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, cons
 
 __global__ void dc_permute_kernel(StedcWs ws, int lev, const double* __restrict__ Zin, int ldin, long long sin,
                                   double* __restrict__ Zout, int ldout, long long sout, double* __restrict__ w,
-                                  long long stride_w, int* __restrict__ info, int nvec, const int* __restrict__ map) {
+                                  long long stride_w, int* __restrict__ info, int nvec, int cpb,
+                                  const int* __restrict__ map) {
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
   const int n = ws.n;
-  const int j = blockIdx.x;
-  const int r = (ws.rank + q * n)[j];
-  const double* x = Zin + q * sin + (size_t)j * ldin;
-  double* y = Zout + q * sout + (size_t)r * ldout;
-  if (r < nvec)  // partial spectrum: the other eigenvectors were never formed
-    for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = x[i];
-  if (threadIdx.x == 0) {
-    const double l = (ws.lam[lev] + q * n)[j] * ws.scale[q];
-    (w + q * stride_w)[r] = l;
-    if (!isfinite(l) && info) info[q] = 1;
+  // one column per block, or (short columns: batches of small matrices) one per warp and cpb per block - see dc_gather
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j_begin = cpb == 1 ? blockIdx.x : blockIdx.x * cpb + warp;
+  const int j_end = cpb == 1 ? blockIdx.x + 1 : min(n, (int)(blockIdx.x + 1) * cpb);
+  const int j_step = cpb == 1 ? 1 : nwarp;
+  const int i0 = cpb == 1 ? threadIdx.x : lane, istep = cpb == 1 ? blockDim.x : 32;
+  for (int j = j_begin; j < j_end && j < n; j += j_step) {
+    const int r = (ws.rank + q * n)[j];
+    const double* x = Zin + q * sin + (size_t)j * ldin;
+    double* y = Zout + q * sout + (size_t)r * ldout;
+    if (r < nvec)  // partial spectrum: the other eigenvectors were never formed
+      for (int i = i0; i < n; i += istep) y[i] = x[i];
+    if (i0 == 0) {
+      const double l = (ws.lam[lev] + q * n)[j] * ws.scale[q];
+      (w + q * stride_w)[r] = l;
+      if (!isfinite(l) && info) info[q] = 1;
+    }
   }
 }
 
@@ -735,8 +751,9 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
       count_launch();
     }
     dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, partial, map);
-    dc_gather_kernel<<<dim3(kmax, nodes, batch), 128, 0, st>>>(ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur],
-                                                              bufp[nxt], bufld[nxt], bufs[nxt], nodes, partial, map);
+    const int gcpb = kmax <= 256 ? 16 : 1;  // columns per block of the gather
+    dc_gather_kernel<<<dim3(ceil_div(kmax, gcpb), nodes, batch), 128, 0, st>>>(
+        ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur], bufp[nxt], bufld[nxt], bufs[nxt], nodes, partial, gcpb, map);
     count_launch(6);
     GSCF_CHECK_LAUNCH();
     GemmParams gp{};
@@ -748,8 +765,9 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
   }
   // ---- final ascending order ----------------------------------------------------------------------------
   dc_rank_kernel<<<dim3(std::max(1, ceil_div(n, 128)), batch), 128, 0, st>>>(ws, lev, info_dev, map);
-  dc_permute_kernel<<<dim3(n, batch), 128, 0, st>>>(ws, lev, bufp[cur], bufld[cur], bufs[cur], Z, ldz, strideZ, w,
-                                                    stride_w, info_dev, nv, map);
+  const int pcpb = n <= 256 ? 16 : 1;
+  dc_permute_kernel<<<dim3(ceil_div(n, pcpb), batch), 128, 0, st>>>(ws, lev, bufp[cur], bufld[cur], bufs[cur], Z, ldz,
+                                                                   strideZ, w, stride_w, info_dev, nv, pcpb, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   return GSCF_B200_OK;
