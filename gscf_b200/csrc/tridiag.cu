@@ -836,14 +836,26 @@ int tridiagonalise(int n, double* A, int lda, long long sA, const TrdWs& ws, int
 
 // ---- back-transformation ---------------------------------------------------------------------------------------
 // All reflectors as a unit lower trapezoidal matrix with explicit zeros: Vf(:, c) = [0 .. 0, 1, v_c], unit at row c+1.
-__global__ void extract_v_all_kernel(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws,
+// cpb columns per block (blockIdx.y indexes column chunks): short columns (batches of small matrices) take one warp per
+// column, a block per column was bound by the block scheduling rate there.
+__global__ void extract_v_all_kernel(const double* __restrict__ Ab, int lda, long long sA, TrdWs ws, int cpb,
                                      const int* __restrict__ map) {
   const long long q = map ? map[blockIdx.z] : blockIdx.z;
-  const int n = ws.n, c = blockIdx.y;
-  const double* a = Ab + q * sA + (size_t)c * lda;
-  double* v = ws.Vf + q * (long long)ws.ld * n + (size_t)c * ws.ld;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
-    v[r] = (c >= n - 1 || r <= c) ? 0.0 : (r == c + 1 ? 1.0 : a[r]);
+  const int n = ws.n;
+  if (cpb == 1) {
+    const int c = blockIdx.y;
+    const double* a = Ab + q * sA + (size_t)c * lda;
+    double* v = ws.Vf + q * (long long)ws.ld * n + (size_t)c * ws.ld;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+      v[r] = (c >= n - 1 || r <= c) ? 0.0 : (r == c + 1 ? 1.0 : a[r]);
+    return;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = blockIdx.y * cpb + warp; c < min(n, (int)(blockIdx.y + 1) * cpb); c += nwarp) {
+    const double* a = Ab + q * sA + (size_t)c * lda;
+    double* v = ws.Vf + q * (long long)ws.ld * n + (size_t)c * ws.ld;
+    for (int r = lane; r < n; r += 32) v[r] = (c >= n - 1 || r <= c) ? 0.0 : (r == c + 1 ? 1.0 : a[r]);
+  }
 }
 
 // descriptors of the per-block set-up GEMMs: which = 0: G_b = V_b^T V_b,  1: W_b = V_b T_b
@@ -920,7 +932,10 @@ int back_transform_setup(int n, const double* A, int lda, long long sA, const Tr
                          cudaStream_t st) {
   if (n < 2) return GSCF_B200_OK;
   const int nblocks = ws.nbq;
-  extract_v_all_kernel<<<dim3(std::max(1, std::min(8, ceil_div(n, 256))), n, batch), 256, 0, st>>>(A, lda, sA, ws, map);
+  if (n <= 256)
+    extract_v_all_kernel<<<dim3(1, ceil_div(n, 32), batch), 256, 0, st>>>(A, lda, sA, ws, 32, map);
+  else
+    extract_v_all_kernel<<<dim3(std::max(1, std::min(8, ceil_div(n, 256))), n, batch), 256, 0, st>>>(A, lda, sA, ws, 1, map);
   bt_desc_kernel<<<ceil_div(batch * nblocks, 128), 128, 0, st>>>(ws, 0, batch, map);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
