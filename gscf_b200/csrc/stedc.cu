@@ -132,11 +132,11 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
   const double eps = 2.220446049250313e-16;
   for (int l = 0; l < m; ++l) {
     for (int iter = 0; iter < 60; ++iter) {
-      int mm = l;
-      for (; mm < m - 1; ++mm) {
-        const double dd = fabs(sd[mm]) + fabs(sd[mm + 1]);
-        if (fabs(se[mm]) <= eps * dd) break;
-      }
+      // first negligible off-diagonal entry at or after l: every lane tests its own entry, one ballot (the serial scan
+      // was a chain of up to m dependent shared-memory loads per QL iteration)
+      const bool small = lane < m - 1 && fabs(se[lane]) <= eps * (fabs(sd[lane]) + fabs(sd[lane + 1]));
+      const unsigned cand = __ballot_sync(0xffffffffu, small) & (0xffffffffu << l);
+      const int mm = cand ? min(m - 1, __ffs(cand) - 1) : m - 1;
       if (mm == l) break;
       const double dl = sd[l], el = se[l];
       double g = (sd[l + 1] - dl) / (2.0 * el);
@@ -146,8 +146,12 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
       double sn = 1.0, cs = 1.0, p = 0.0;
       int i = mm - 1;
       bool underflow = false;
+      // the entries of step i are loaded one step ahead (d[i + 1] of the next step is this step's d[i]): their
+      // shared-memory latency is off the recurrence; a sweep only writes entries it has already read
+      double ei = se[i], di1 = sd[i + 1], di = sd[i];
       for (; i >= l; --i) {
-        const double ei = se[i], di1 = sd[i + 1], di = sd[i];
+        double ein = 0.0, din = 0.0;
+        if (i > l) { ein = se[i - 1]; din = sd[i - 1]; }
         __syncwarp();  // every lane has read this step's entries before lane 0 overwrites them
         const double f = sn * ei, b = cs * ei;
         // r = sqrt(x), 1 / r as ONE reciprocal square root (1 ulp) and a product: the sqrt + divide chain was a third of
@@ -175,6 +179,7 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
           Zs[(i + 1) * kLeaf + lane] = sn * z0 + cs * z1;
           Zs[i * kLeaf + lane] = cs * z0 - sn * z1;
         }
+        di1 = di; di = din; ei = ein;
       }
       __syncwarp();
       if (!underflow) {
@@ -205,7 +210,7 @@ __global__ void zero_matrix_kernel(double* __restrict__ Z, int ldz, long long sZ
 
 // ---- merge: prepare / deflate ------------------------------------------------------------------------
 // dynamic shared memory: k * (4 doubles + 4 ints) when it fits, otherwise the global work arrays
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 dc_prepare_kernel(StedcWs ws, const double* __restrict__ e, long long dstride, int h, int lev_in,
                   double* __restrict__ Zin, int ldin, long long sin, int use_smem,
                   const int* __restrict__ map) {
@@ -460,10 +465,20 @@ dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
   const double* S = ws.S + q * (long long)ws.ld * n + (size_t)lo * ws.ld + lo;
   const double* dl = ws.dlamda + q * n + lo;
   const double dj = dl[j];
+  // four factors per division (the kernel was bound by its K^2 FP64 divisions: 0.6 of 6.7 ms of a C4 divide & conquer): T
+  // has unit max-norm and deflation keeps |d_j - d_i| and |delta| above ~1e-30, so products of four cannot leave the range
   double p = 1.0;
-  for (int i = lane; i < K; i += 32) {
-    const double del = S[(size_t)j * ws.ld + i];
-    p *= (i == j) ? del : del / (dj - dl[i]);
+  for (int i0 = lane; i0 < K; i0 += 128) {
+    double num = 1.0, den = 1.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < K) {
+        num *= S[(size_t)j * ws.ld + i];
+        if (i != j) den *= dj - dl[i];
+      }
+    }
+    p *= num / den;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
@@ -471,9 +486,10 @@ dc_zhat_kernel(StedcWs ws, int h, const int* __restrict__ map) {
 }
 
 // U^T[gpos[j]][i] = zhat_j / delta(j,i) / ||.||.  CTA = 32 eigenvectors (lane) x 8 warps splitting the poles.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 dc_vectors_kernel(StedcWs ws, int h, int partial, const int* __restrict__ map) {
-  __shared__ double snrm[8][33];
+  __shared__ double snrm[32][33];
+  const int nw = blockDim.x >> 5;  // 8 warps, or 32 when a level has few large merges (K / 32 CTAs would not fill the GPU)
   const int t = blockIdx.y, zb = blockIdx.z;
   const long long q = map ? map[zb] : zb;
   const int n = ws.n;
@@ -492,7 +508,7 @@ dc_vectors_kernel(StedcWs ws, int h, int partial, const int* __restrict__ map) {
   // pass 1: unnormalised components (one division each) into U, norms; pass 2: scale in place (same thread, same entries)
   double nrm = 0.0;
   if (i < Kv)
-    for (int j = warp; j < K; j += 8) {
+    for (int j = warp; j < K; j += nw) {
       const double u = zh[j] / S[(size_t)j * ws.ld + i];
       U[(size_t)gpos[j] * ws.ld + i] = u;
       nrm = fma(u, u, nrm);
@@ -500,11 +516,10 @@ dc_vectors_kernel(StedcWs ws, int h, int partial, const int* __restrict__ map) {
   snrm[warp][lane] = nrm;
   __syncthreads();
   double tot = 0.0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) tot += snrm[w][lane];
+  for (int w = 0; w < nw; ++w) tot += snrm[w][lane];
   const double inv = 1.0 / sqrt(tot);
   if (i < Kv)
-    for (int j = warp; j < K; j += 8) U[(size_t)gpos[j] * ws.ld + i] *= inv;
+    for (int j = warp; j < K; j += nw) U[(size_t)gpos[j] * ws.ld + i] *= inv;
 }
 
 // Partial spectrum (n_eigenpairs = nvec < n, ScfBase.hh:87,315-316): at the TOP-LEVEL merge only the eigenvectors of
@@ -595,19 +610,36 @@ dc_gather_kernel(StedcWs ws, int h, int lev_out, const double* __restrict__ Zin,
 }
 
 // ---- final ascending sort -----------------------------------------------------------------------------
-__global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, const int* __restrict__ map) {
+// wpj == 0: one thread per entry (batches of small matrices); wpj == 1: one WARP per entry, the lanes split the n
+// comparisons (one large matrix: 1024 threads walking 1024 entries each took 54 us of a 5.7 ms iteration at n = 1024)
+__global__ void dc_rank_kernel(StedcWs ws, int lev, int* __restrict__ info, int wpj, const int* __restrict__ map) {
   const long long q = map ? map[blockIdx.y] : blockIdx.y;
   const int n = ws.n;
   const double* lam = ws.lam[lev] + q * n;
   int* rank = ws.rank + q * n;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const long long lj = dc_sort_key(lam[j]);
-    int r = 0;
-    for (int i = 0; i < n; ++i) {
-      const long long li = dc_sort_key(lam[i]);
-      r += (li < lj || (li == lj && i < j)) ? 1 : 0;
+  if (wpj) {
+    const int lane = threadIdx.x & 31, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += nw) {
+      const long long lj = dc_sort_key(lam[j]);
+      int r = 0;
+      for (int i = lane; i < n; i += 32) {
+        const long long li = dc_sort_key(lam[i]);
+        r += (li < lj || (li == lj && i < j)) ? 1 : 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+      if (lane == 0) rank[j] = r;
     }
-    rank[j] = r;
+  } else {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+      const long long lj = dc_sort_key(lam[j]);
+      int r = 0;
+      for (int i = 0; i < n; ++i) {
+        const long long li = dc_sort_key(lam[i]);
+        r += (li < lj || (li == lj && i < j)) ? 1 : 0;
+      }
+      rank[j] = r;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && info) info[q] = 0;
 }
@@ -726,8 +758,15 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
     const int nxt = 1 - cur;
     const size_t smem = (size_t)kmax * 48;
     const int use_smem = smem <= 200 * 1024 ? 1 : 0;
-    zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[nxt], bufld[nxt], bufs[nxt], n, map);
-    dc_prepare_kernel<<<dim3(nodes, batch), 256, use_smem ? smem : 0, st>>>(ws, e, dstride, h, lev, bufp[cur],
+    // the top-level merge writes every column of its (single) n x n block - roots by the GEMMs, deflated columns by the
+    // gather; lower levels leave the blocks between the nodes to this zero fill
+    if (h < L || nv < n) {
+      zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[nxt], bufld[nxt], bufs[nxt], n, map);
+      count_launch(1);
+    }
+    // the O(k^2) rank sort of a large merge: 1024 threads when there are few merges to fill the GPU with
+    const int prep_t = (kmax >= 512 && nodes * batch <= 148) ? 1024 : 256;
+    dc_prepare_kernel<<<dim3(nodes, batch), prep_t, use_smem ? smem : 0, st>>>(ws, e, dstride, h, lev, bufp[cur],
                                                                             bufld[cur], bufs[cur], use_smem, map);
     // a warp per root (latency: one large merge) or a thread per root (throughput: many small merges)
     static int sec_mode = -1;  // 0 auto, 1 warp, 2 thread
@@ -750,11 +789,12 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
       dc_select_kernel<<<batch, 256, 0, st>>>(ws, 1 - lev, nv, map);
       count_launch();
     }
-    dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), 256, 0, st>>>(ws, h, partial, map);
+    const int vec_t = (kmax >= 512 && (long long)ceil_div(kmax, 32) * nodes * batch <= 148) ? 1024 : 256;
+    dc_vectors_kernel<<<dim3(ceil_div(kmax, 32), nodes, batch), vec_t, 0, st>>>(ws, h, partial, map);
     const int gcpb = kmax <= 256 ? 16 : 1;  // columns per block of the gather
     dc_gather_kernel<<<dim3(ceil_div(kmax, gcpb), nodes, batch), 128, 0, st>>>(
         ws, h, 1 - lev, bufp[cur], bufld[cur], bufs[cur], bufp[nxt], bufld[nxt], bufs[nxt], nodes, partial, gcpb, map);
-    count_launch(6);
+    count_launch(5);
     GSCF_CHECK_LAUNCH();
     GemmParams gp{};
     gp.descs = ws.descs;
@@ -764,7 +804,10 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
     lev = 1 - lev;
   }
   // ---- final ascending order ----------------------------------------------------------------------------
-  dc_rank_kernel<<<dim3(std::max(1, ceil_div(n, 128)), batch), 128, 0, st>>>(ws, lev, info_dev, map);
+  if (n > 256 && batch <= 16)
+    dc_rank_kernel<<<dim3(std::max(1, std::min(ceil_div(n, 4), 592 / batch)), batch), 128, 0, st>>>(ws, lev, info_dev, 1, map);
+  else
+    dc_rank_kernel<<<dim3(std::max(1, ceil_div(n, 128)), batch), 128, 0, st>>>(ws, lev, info_dev, 0, map);
   const int pcpb = n <= 256 ? 16 : 1;
   dc_permute_kernel<<<dim3(ceil_div(n, pcpb), batch), 128, 0, st>>>(ws, lev, bufp[cur], bufld[cur], bufs[cur], Z, ldz,
                                                                    strideZ, w, stride_w, info_dev, nv, pcpb, map);

@@ -306,14 +306,15 @@ trd_fused_kernel(const TfArgs a) {
             const double2 vn = *reinterpret_cast<const double2*>(svc + r);  // v_j
 #pragma unroll
             for (int u = 0; u < TF_CG; ++u) {
-              if (u >= s0 && u < S) {
-                double2 x = ra[REGA ? u : 0][REGA ? p : 0];
-                x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
-                x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
-                ra[REGA ? u : 0][REGA ? p : 0] = x;
-                if (pub_raw && u == s0) *reinterpret_cast<double2*>(Xr + r) = x;
-                acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
-              }
+              // no test per column: a finished column (u < s0) only sees zeros of v_{j-1} / w_{j-1} (or one last update it
+              // no longer needs) and its sum is never read, a column beyond S is zero and stays zero - a branch per column
+              // kept the compiler from interleaving the eight FMA chains
+              double2 x = ra[REGA ? u : 0][REGA ? p : 0];
+              x.x = fma(-vp.x, wc[u], fma(-wp.x, vc[u], x.x));
+              x.y = fma(-vp.y, wc[u], fma(-wp.y, vc[u], x.y));
+              ra[REGA ? u : 0][REGA ? p : 0] = x;
+              if (pub_raw && u == s0) *reinterpret_cast<double2*>(Xr + r) = x;
+              acc[u] = fma(x.x, vn.x, fma(x.y, vn.y, acc[u]));
             }
           }
         }
@@ -645,17 +646,25 @@ trd_fused_kernel(const TfArgs a) {
 // NMAX = 64 (thread (cg = tid / 32, pr = tid % 32), columns cg + 8 u, NU = 8) is the same kernel for orders <= 64, and
 // the driver hands the trailing 64 x 64 block of a larger matrix over to it (jstop, see TfArgs) - measured on B200,
 // 4096 matrices of order 128: see DESIGN.md section 5.
-template <int NMAX>
-__global__ void __launch_bounds__(256, 1)
+// T = 512 (NMAX = 128 only: 64 row pairs x 8 column groups, NU = 16): the 256-thread layout issues ~920 instructions per
+// warp and column with two warps per scheduler and stalls on fixed-latency dependencies (ncu: 35 % issue utilisation,
+// `profiles/r02_ncu_full_solo_reg.json`); twice the warps at half the registers hide them.
+template <int NMAX, int T = 256>
+__global__ void __launch_bounds__(T, NMAX == 64 ? 2 : 1)  // the 64-row layout runs two CTAs per SM (<= 128 registers)
 trd_solo_reg_kernel(const TfArgs a) {
   static_assert(NMAX == 128 || NMAX == 64, "layouts: 64 row pairs x 4 column groups, or 32 row pairs x 8 column groups");
+  static_assert(T == 256 || (T == 512 && NMAX == 128), "thread counts");
+  constexpr int NWARP = T / 32;
   constexpr int RPAIRS = NMAX / 2;           // row pairs = threads per column group
-  constexpr int NCG = 256 / RPAIRS;          // column groups (4 / 8)
-  constexpr int NU = NMAX / NCG;             // columns per thread (32 / 8)
+  constexpr int NCG = T / RPAIRS;            // column groups (4 / 8)
+  constexpr int NU = NMAX / NCG;             // columns per thread (32 / 16 / 8)
   constexpr int WPG = RPAIRS / 32;           // warps per column group (2 / 1)
   __shared__ __align__(16) double sv0[NMAX], sv1[NMAX], sw[NMAX], sraw[NMAX];
-  __shared__ double spart[8][NU + 1];
-  __shared__ double sred1[8], sred2[8], sbc[8];
+  // {w_{j-1}(c), v_{j-1}(c)} of the sweep, grouped by column group: entry (c % NCG) NU + c / NCG - a thread reads the pairs
+  // of its NU columns as consecutive 16-byte (warp-uniform) loads instead of two strided 8-byte loads per column
+  __shared__ __align__(16) double2 spair[NMAX];
+  __shared__ double spart[NWARP][NU + 1];
+  __shared__ double sred1[NWARP], sred2[NWARP], sbc[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cg = tid / RPAIRS, pr = tid % RPAIRS, r0 = 2 * pr;
   const long long q = a.map ? a.map[blockIdx.y + a.mat0] : (long long)blockIdx.y + a.mat0;
@@ -673,7 +682,7 @@ trd_solo_reg_kernel(const TfArgs a) {
     }
     ra[u] = v;
   }
-  if (tid < NMAX) { sv0[tid] = 0.0; sv1[tid] = 0.0; sw[tid] = 0.0; sraw[tid] = 0.0; }
+  if (tid < NMAX) { sv0[tid] = 0.0; sv1[tid] = 0.0; sw[tid] = 0.0; sraw[tid] = 0.0; spair[tid] = make_double2(0.0, 0.0); }
   if (tid < 8) sbc[tid] = 0.0;
   __syncthreads();
 
@@ -686,7 +695,7 @@ trd_solo_reg_kernel(const TfArgs a) {
     __syncthreads();
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w];
+    for (int w = 0; w < NWARP; ++w) s += red[w];
     return s;
   };
   const int jlast = (a.jstop > 0 && a.jstop <= n - 2) ? a.jstop - 1 : n - 2;
@@ -700,68 +709,69 @@ trd_solo_reg_kernel(const TfArgs a) {
       const double2 vp = *reinterpret_cast<const double2*>(svn + r0);
       const double2 wp = *reinterpret_cast<const double2*>(sw + r0);
       const double2 vn = *reinterpret_cast<const double2*>(svc + r0);
-      double acc[NU];
+      // Chunks of eight columns per thread, skipped as a whole (uniform test) once all their columns are finished; inside
+      // a chunk no test per column: a finished column only sees the zeros of v_{j-1} / w_{j-1} (column `first - 1` one last
+      // update it no longer needs) and its sum is never read, columns >= n are zero and stay zero.  (ncu of the per-column
+      // test, `profiles/r02_ncu_full_solo_reg.json`: a quarter of the executed instructions were BSSY / BSYNC / BRA / ISETP,
+      // and every column was its own basic block - no interleaving of the FMA chains, 2.3 warps per issue waiting.)
+      // The warp-wide sums are formed chunk by chunk (8 values -> 1 per lane with three halving steps over lane bits
+      // 16 / 8 / 4: every step halves the values a lane is responsible for), then the chunks are folded over lane bits
+      // 2 / 1: only eight accumulators are live at a time (the 255-register build of the all-at-once butterfly had no
+      // room to hoist the shared-memory loads of w(c) / v(c) away from their FMAs), a finished chunk costs nothing.
+      constexpr int NCH = NU / 8;
+      const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+      double bch[NCH];
 #pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int c = cg + NCG * u;
-        double s = 0.0;
-        if (c >= first && c < n) {
-          const double wc = sw[c], vc = svn[c];
-          double2 x = ra[u];
-          x.x = fma(-vp.x, wc, fma(-wp.x, vc, x.x));
-          x.y = fma(-vp.y, wc, fma(-wp.y, vc, x.y));
-          ra[u] = x;
-          if (c == first) *reinterpret_cast<double2*>(sraw + r0) = x;
-          s = fma(x.x, vn.x, x.y * vn.y);
+      for (int ch = 0; ch < NCH; ++ch) {
+        bch[ch] = 0.0;
+        if (NCG * (8 * ch + 8) > first) {  // the chunk's last column, NCG (8 ch + 7) + NCG - 1, is still alive
+          double acc[8];
+          double2 wvc[8];
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) wvc[u8] = spair[cg * NU + 8 * ch + u8];
+#pragma unroll
+          for (int u8 = 0; u8 < 8; ++u8) {
+            const int u = 8 * ch + u8;
+            const int c = cg + NCG * u;
+            const double wc = wvc[u8].x, vc = wvc[u8].y;
+            double2 x = ra[u];
+            x.x = fma(-vp.x, wc, fma(-wp.x, vc, x.x));
+            x.y = fma(-vp.y, wc, fma(-wp.y, vc, x.y));
+            ra[u] = x;
+            if (c == first) *reinterpret_cast<double2*>(sraw + r0) = x;
+            acc[u8] = fma(x.x, vn.x, x.y * vn.y);
+          }
+          double a4[4], a2[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+            a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+            a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          bch[ch] = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
         }
-        acc[u] = s;
       }
-      if constexpr (NU == 32) {
-        // 32 sums over the 32 lanes: each butterfly step halves the values a lane keeps; lane L ends with the sum of acc[L]
-        double a16[16], a8[8], a4[4], a2[2];
-        {
-          const bool h = lane & 16;
+      // bch[ch]: column u = 8 ch + w of my column group, w = 4 h16 + 2 h8 + h4, summed over 8 of the warp's 32 row pairs
+      const int w8 = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+      if constexpr (NCH == 4) {
+        double c2[2];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a16[i] = (h ? acc[i + 16] : acc[i]) + __shfl_xor_sync(0xffffffffu, h ? acc[i] : acc[i + 16], 16);
-        }
-        {
-          const bool h = lane & 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a8[i] = (h ? a16[i + 8] : a16[i]) + __shfl_xor_sync(0xffffffffu, h ? a16[i] : a16[i + 8], 8);
-        }
-        {
-          const bool h = lane & 4;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) a4[i] = (h ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h ? a8[i] : a8[i + 4], 4);
-        }
-        {
-          const bool h = lane & 2;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) a2[i] = (h ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h ? a4[i] : a4[i + 2], 2);
-        }
-        const bool h1 = lane & 1;
-        const double tot = (h1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? a2[0] : a2[1], 1);
-        spart[warp][lane] = tot;  // u = lane, rows of this warp (two warps per column group)
+        for (int i = 0; i < 2; ++i) c2[i] = (h2 ? bch[i + 2] : bch[i]) + __shfl_xor_sync(0xffffffffu, h2 ? bch[i] : bch[i + 2], 2);
+        const double tot = (h1 ? c2[1] : c2[0]) + __shfl_xor_sync(0xffffffffu, h1 ? c2[0] : c2[1], 1);
+        spart[warp][8 * ((h2 ? 2 : 0) + (h1 ? 1 : 0)) + w8] = tot;
+      } else if constexpr (NCH == 2) {
+        double tot = (h2 ? bch[1] : bch[0]) + __shfl_xor_sync(0xffffffffu, h2 ? bch[0] : bch[1], 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if (!h1) spart[warp][8 * (h2 ? 1 : 0) + w8] = tot;
       } else {
-        // 8 sums over the 32 lanes (the warp holds ALL rows of its column group): lanes 0, 4, ... 28 end with column u = lane / 4
-        static_assert(NU == 32 || NU == 8, "butterflies are written for 32 and 8 accumulators");
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-        double a4[4], a2[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
-          a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
-          a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-        const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
-        if ((lane & 3) == 0) spart[warp][u] = a1;
+        static_assert(NCH == 1 || NCH == 2 || NCH == 4, "8, 16 or 32 columns per thread");
+        double tot = bch[0] + __shfl_xor_sync(0xffffffffu, bch[0], 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if ((lane & 3) == 0) spart[warp][w8] = tot;
       }
       __syncthreads();
       if (tid < n) {
@@ -807,6 +817,7 @@ trd_solo_reg_kernel(const TfArgs a) {
       const double vcur = svc[r];
       svn[r] = vnew;
       sw[r] = wv;
+      spair[(r % NCG) * NU + r / NCG] = make_double2(wv, vcur);  // (w_j, v_j): the reflector the next sweep applies
       if (j >= 0 && r > first) A[(size_t)j * lda + r] = vcur;  // reflector j, LAPACK layout
     }
     __syncthreads();

@@ -673,7 +673,10 @@ int tf_phase(int n, int n_full, double* A, int lda, long long sA, const TrdWs& w
       if (solo_reg) {
         // the register layout is fixed per instantiation: orders <= 64 (and the trailing block a larger matrix hands over)
         // run the 64-row layout, whose column step costs less than half of the 128-row one
+        static int solo_reg_t = -1;
+        if (solo_reg_t < 0) { const char* srt = getenv("GSCF_B200_TF_SOLO_REG_T"); solo_reg_t = srt ? atoi(srt) : 256; }
         if (n <= 64) trd_solo_reg_kernel<64><<<dim3(1, cnt), 256, 0, st>>>(a);
+        else if (solo_reg_t == 512) trd_solo_reg_kernel<128, 512><<<dim3(1, cnt), 512, 0, st>>>(a);
         else trd_solo_reg_kernel<128><<<dim3(1, cnt), 256, 0, st>>>(a);
         count_launch();
         GSCF_CHECK_LAUNCH();
