@@ -38,6 +38,29 @@ inline size_t tfb_smem_bytes(int n) {
   return ((size_t)3 * np + 32 * TF_MAXS + 32 + 32 + 8 + 2 * TFB_PW * TF_MAXS + 2 * TFB_PW) * sizeof(double);
 }
 
+// Eight sums over the warp with 7 exchanges instead of 40 (every butterfly step halves the values a lane is responsible
+// for): lanes 0, 4, ... 28 end with the sum of acc[lane / 4] and store it to out[lane / 4] if that index is < nvalid.
+__device__ __forceinline__ void tfb_butterfly8(const double (&acc)[TF_CG], int lane, int nvalid, double* out) {
+  static_assert(TF_CG == 8, "written for 8 accumulators");
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  double a4[4], a2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = h16 ? acc[i] : acc[i + 4], keep = h16 ? acc[i + 4] : acc[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  const int u = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+  if ((lane & 3) == 0 && u < nvalid) out[u] = a1;
+}
+
 template <int KMAX, int T>
 __global__ void __launch_bounds__(T, 1)
 trd_fused_blocked_kernel(const TfbArgs ab) {
@@ -245,11 +268,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
               }
             }
           }
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) {
-            const double s = warp_sum(acc[u]);
-            if (lane == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = s;
-          }
+          tfb_butterfly8(acc, lane, S - sg, spart + warp * TF_MAXS + sg);
         }
         j0 = j;
         TFB_TICK(1);
@@ -284,11 +303,7 @@ trd_fused_blocked_kernel(const TfbArgs ab) {
               acc[u] = fma(x1[u].x, v1.x, fma(x1[u].y, v1.y, acc[u]));
             }
           }
-#pragma unroll
-          for (int u = 0; u < TF_CG; ++u) {
-            const double s = warp_sum(acc[u]);
-            if (lane == 0 && sg + u < S) spart[warp * TF_MAXS + sg + u] = s;
-          }
+          tfb_butterfly8(acc, lane, S - sg, spart + warp * TF_MAXS + sg);
         }
       }
       TFB_TICK(2);
