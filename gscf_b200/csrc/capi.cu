@@ -14,6 +14,7 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* last_error_cstr() { return g_last_error.c_str(); }
 uint64_t launch_count_value();
+uint64_t tensor_map_launch_count_value();
 
 static int have_device() {
   int ndev = 0;
@@ -76,6 +77,7 @@ extern "C" {
 const char* gscf_b200_last_error(void) { return last_error_cstr(); }
 const char* gscf_b200_version_string(void) { return "gscf-b200 0.1.0 (sm_100a)"; }
 uint64_t gscf_b200_launch_count(void) { return launch_count_value(); }
+uint64_t gscf_b200_tensor_map_launch_count(void) { return tensor_map_launch_count_value(); }
 
 int gscf_b200_dgemm(int transa, int transb, int m, int n, int k, double alpha, const double* A, int lda,
                     long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,

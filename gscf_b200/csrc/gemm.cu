@@ -7,10 +7,20 @@
 // per-lane DMMA fragment reads are bank-conflict free:
 //     !TA: sA[k][m]  ld = BM+4      TA: sA[m][k]  ld = BK+4
 //     !TB: sB[n][k]  ld = BK+4      TB: sB[k][n]  ld = BN+4
+//
+// k-contiguous operands (TA / !TB: X^T Z, V^T Z, the right-hand operands of every NN product) of launches whose
+// shapes qualify are staged by TENSOR-MAP TMA instead (cp.async.bulk.tensor, SASS UTMALDG; kernel
+// dgemm_dmma_tm_kernel): a 3-D map {k, rows, batch entry} with boxes of 4 x BM (x 1) doubles lands one k-group of
+// the tile densely as s[kgroup][row][4], so the 32 lanes of a DMMA fragment (row = lane / 4, k = lane % 4) read 256
+// consecutive bytes - conflict-free without padding, which a tensor-map box cannot produce.  The m- / n-contiguous
+// operand of the same launch keeps its 1-D bulk copies; all copies of a stage complete on the stage's one mbarrier.
 #include "gemm.cuh"
+
+#include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled types (the entry point is fetched at run time)
 
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 
 namespace gscfb {
 
@@ -18,7 +28,7 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
 
-template <int BM, int BN, int BK, bool TA, bool TB>
+template <int BM, int BN, int BK, bool TA, bool TB, bool TM = false>
 struct SmemLayout {
   static constexpr int A_CE = TA ? BK : BM;  // contiguous extent
   static constexpr int A_SE = TA ? BM : BK;  // strided extent
@@ -26,10 +36,23 @@ struct SmemLayout {
   static constexpr int B_SE = TB ? BK : BN;
   static constexpr int A_LD = A_CE + 4;
   static constexpr int B_LD = B_CE + 4;
-  static constexpr int A_ELEMS = A_SE * A_LD;
-  static constexpr int B_ELEMS = B_SE * B_LD;
+  // TM: a k-contiguous operand is staged by tensor-map TMA as s[k / 4][row][4] (dense)
+  static constexpr bool A_TM = TM && TA;
+  static constexpr bool B_TM = TM && !TB;
+  static constexpr int A_ELEMS = A_TM ? BM * BK : A_SE * A_LD;
+  static constexpr int B_ELEMS = B_TM ? BN * BK : B_SE * B_LD;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static_assert(!TM || (A_ELEMS % 16 == 0 && B_ELEMS % 16 == 0), "TMA destinations stay 128-byte aligned");
 };
+
+// One box of a 3-D tensor map -> shared memory, completing on `bar` (coordinates innermost first).
+__device__ __forceinline__ void tma_tensor3d_g2s(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 
 // Copy one operand tile into shared memory.  CE/SE/LD as in SmemLayout; (c0, s0) = tile origin
 // along the contiguous / strided global direction; (climit, slimit) = matrix extents.
@@ -54,13 +77,12 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
-dgemm_dmma_kernel(const GemmParams p) {
-  using L = SmemLayout<BM, BN, BK, TA, TB>;
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, bool TM>
+__device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB) {
+  using L = SmemLayout<BM, BN, BK, TA, TB, TM>;
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   constexpr int MI = WM / 8, NI = WN / 8;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
 
   // ---- resolve this CTA's problem ---------------------------------------------------------
   const double* A;
@@ -69,6 +91,7 @@ dgemm_dmma_kernel(const GemmParams p) {
   double* C2 = nullptr;
   int m, n, k, lda, ldb, ldc;
   double alpha, beta;
+  int zq = 0;  // batch entry (third tensor-map coordinate of a strided operand)
   if (p.descs != nullptr) {
     const GemmDesc d = p.descs[blockIdx.z];
     A = d.A; B = d.B; C = d.C; m = d.m; n = d.n; k = d.k;
@@ -76,6 +99,7 @@ dgemm_dmma_kernel(const GemmParams p) {
   } else {
     const int ze = p.ksplit > 1 ? blockIdx.z / p.ksplit : blockIdx.z;
     const long long z = p.batch_map ? p.batch_map[ze] : ze;
+    zq = (int)z;
     A = p.A + z * p.sA; B = p.B + z * p.sB; C = p.C + z * p.sC;
     if (p.C2) C2 = p.C2 + z * p.sC2;
     m = p.m; n = p.n; k = p.k; lda = p.lda; ldb = p.ldb; ldc = p.ldc;
@@ -141,8 +165,10 @@ dgemm_dmma_kernel(const GemmParams p) {
   // ... and only when BOTH operands qualify (the NT products: F X^T, C_o C_o^T, the Pulay outer products, Q U^T of the
   // D&C merges, L21 L21^T): mixing the two mechanisms in one stage measured slower than cp.async alone at n = 1024
   // (18.8 vs 23.4 TFLOP/s), both through TMA faster (NT 4096^3: 30.0 vs 25.7 TFLOP/s).
-  const bool both = interior && !TA && TB && alignedA && alignedB;
-  const bool bulkA = both, bulkB = both;
+  // TM kernel: the host has checked shapes and alignment of the whole launch - every CTA takes the TMA path, the
+  // k-contiguous operand(s) through the tensor map(s), the other one through bulk copies
+  const bool both = TM || (interior && !TA && TB && alignedA && alignedB);
+  const bool bulkA = TM ? !TA : both, bulkB = TM ? TB : both;
   const bool use_bulk = both;
   if (use_bulk) {
     if (threadIdx.x == 0) {
@@ -159,7 +185,7 @@ dgemm_dmma_kernel(const GemmParams p) {
     double* sB = sA + L::A_ELEMS;
     const double* Aq = A + (size_t)q * p.skA;
     const double* Bq = B + (size_t)q * p.skB;
-    const unsigned bytes = (unsigned)(((bulkA ? BM : 0) + (bulkB ? BN : 0)) * BK * sizeof(double));
+    const unsigned bytes = (unsigned)(((bulkA || TM ? BM : 0) + (bulkB || TM ? BN : 0)) * BK * sizeof(double));
     // warp 0 issues the bulk copies: expect_tx first, then one copy per tile row
     if (threadIdx.x < 32) {
       fence_proxy_async();  // generic-proxy reads of this stage (ordered by the barrier above) before the async-proxy writes
@@ -171,7 +197,16 @@ dgemm_dmma_kernel(const GemmParams p) {
       if (bulkB)
         for (int r = threadIdx.x; r < L::B_SE; r += 32)
           tma_bulk_g2s(sB + r * L::B_LD, Bq + (size_t)(k0 + r) * ldb + n0, (unsigned)(L::B_CE * sizeof(double)), &s_bar[stage]);
+      if (TM) {
+        // one box of 4 (k) x BM / BN rows per k-group; rows and k beyond the matrix are zero-filled by the TMA unit and
+        // still count as full boxes towards the expected bytes
+        if (L::A_TM && threadIdx.x < BK / 4)
+          tma_tensor3d_g2s(sA + threadIdx.x * (BM * 4), tmA, k0 + 4 * (int)threadIdx.x, m0, p.sA != 0 ? zq : 0, &s_bar[stage]);
+        if (L::B_TM && threadIdx.x < BK / 4)
+          tma_tensor3d_g2s(sB + threadIdx.x * (BN * 4), tmB, k0 + 4 * (int)threadIdx.x, n0, p.sB != 0 ? zq : 0, &s_bar[stage]);
+      }
     }
+    if (TM) return;
     // the other operand (k-contiguous rows) through cp.async
     if (!bulkA) {
       if (TA) {
@@ -229,12 +264,12 @@ dgemm_dmma_kernel(const GemmParams p) {
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         const int r = wm + i * 8 + lr;
-        af[i] = TA ? sA[r * L::A_LD + kk + lc] : sA[(kk + lc) * L::A_LD + r];
+        af[i] = L::A_TM ? sA[((kk >> 2) * BM + r) * 4 + lc] : TA ? sA[r * L::A_LD + kk + lc] : sA[(kk + lc) * L::A_LD + r];
       }
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int c = wn + j * 8 + lr;
-        bf[j] = TB ? sB[(kk + lc) * L::B_LD + c] : sB[c * L::B_LD + kk + lc];
+        bf[j] = L::B_TM ? sB[((kk >> 2) * BN + c) * 4 + lc] : TB ? sB[(kk + lc) * L::B_LD + c] : sB[c * L::B_LD + kk + lc];
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
@@ -309,9 +344,109 @@ dgemm_dmma_kernel(const GemmParams p) {
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+dgemm_dmma_kernel(const GemmParams p) {
+  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, false>(p, nullptr, nullptr);
+}
+
+// the same tiles with the k-contiguous operand(s) fed by tensor-map TMA (maps live in the kernel's parameter space)
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+dgemm_dmma_tm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, true>(p, &tmA, &tmB);
+}
+
+// ---- host side of the tensor-map path ------------------------------------------------------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static std::atomic<uint64_t> g_tmap_launches{0};
+uint64_t tensor_map_launch_count_value() { return g_tmap_launches.load(std::memory_order_relaxed); }
+
+// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda); nullptr: driver without it
+static TmapEncodeFn tmap_encode_fn() {
+  static std::atomic<int> state{0};  // 0: not looked up, 1: found, 2: missing
+  static std::atomic<void*> fn{nullptr};
+  if (state.load(std::memory_order_acquire) == 0) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    (void)cudaGetLastError();
+    fn.store(f, std::memory_order_relaxed);
+    state.store(f ? 1 : 2, std::memory_order_release);
+  }
+  return reinterpret_cast<TmapEncodeFn>(fn.load(std::memory_order_relaxed));
+}
+
+// {k (contiguous), rows, batch entries} over a k-contiguous operand; box 4 x box_rows x 1
+static bool encode_kmajor_map(CUtensorMap* tm, const double* base, int k, int rows, int ld, long long stride, int box_rows,
+                              int entries) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, stride != 0 ? (cuuint64_t)entries : 1};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double),
+                                 stride != 0 ? (cuuint64_t)stride * sizeof(double) : (cuuint64_t)ld * sizeof(double) * (cuuint64_t)rows};
+  const cuuint32_t box[3] = {4, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool aligned16(const void* ptr, int ld, long long stride) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld & 1) == 0 && (stride & 1) == 0;
+}
+
+// Does this launch qualify for the tensor-map kernel?  (Whole-launch decision: every CTA then takes the TMA path.)
+template <int BM, int BN, int BK, bool TA, bool TB>
+static bool tm_eligible(const GemmParams& p) {
+  if (!(TA || !TB)) return false;                    // NT products have no k-contiguous operand: 1-D bulk copies
+  if (p.use_tma < 2 || p.descs != nullptr || p.kbatch != 1) return false;
+  if (p.m <= 0 || p.n <= 0 || p.k <= 0) return false;
+  if (!aligned16(p.A, p.lda, p.sA) || !aligned16(p.B, p.ldb, p.sB)) return false;
+  if (p.sA < 0 || p.sB < 0 || p.sA >= (1LL << 36) || p.sB >= (1LL << 36)) return false;
+  // an operand staged by 1-D bulk copies has no zero fill: full tiles along its contiguous direction and along k
+  if (!TA && (p.m % BM != 0 || p.k % BK != 0)) return false;
+  if (TB && (p.n % BN != 0 || p.k % BK != 0)) return false;
+  return true;
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
 static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cudaStream_t st) {
-  using L = SmemLayout<BM, BN, BK, TA, TB>;
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  dim3 grid(ceil_div(max_m, BM), ceil_div(max_n, BN), batch);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return GSCF_B200_OK;
+  if constexpr (TA || !TB) {
+    if (tm_eligible<BM, BN, BK, TA, TB>(p)) {
+      CUtensorMap tmA, tmB;
+      memset(&tmA, 0, sizeof(tmA));
+      memset(&tmB, 0, sizeof(tmB));
+      bool ok = true;
+      // batch extent of the map: only bounds the zero fill; an index-mapped batch may address any problem of the engine
+      const int entries = p.batch_map ? 65536 : batch;
+      if (TA) ok = ok && encode_kmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, entries);
+      if (!TB) ok = ok && encode_kmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, entries);
+      if (ok) {
+        using L = SmemLayout<BM, BN, BK, TA, TB, true>;
+        const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
+        auto kern = dgemm_dmma_tm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
+        static PerDeviceOnce once;
+        int dev;
+        if (once.need(dev)) {
+          GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          once.done(dev);
+        }
+        kern<<<grid, NT, smem, st>>>(p, tmA, tmB);
+        count_launch();
+        g_tmap_launches.fetch_add(1, std::memory_order_relaxed);
+        GSCF_CHECK_LAUNCH();
+        return GSCF_B200_OK;
+      }
+    }
+  }
+  using L = SmemLayout<BM, BN, BK, TA, TB>;
   const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
   auto kern = dgemm_dmma_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
   static PerDeviceOnce once;
@@ -320,8 +455,6 @@ static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cuda
     GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once.done(dev);
   }
-  dim3 grid(ceil_div(max_m, BM), ceil_div(max_n, BN), batch);
-  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return GSCF_B200_OK;
   kern<<<grid, NT, smem, st>>>(p);
   count_launch();
   GSCF_CHECK_LAUNCH();
@@ -406,8 +539,10 @@ int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, i
     set_last_error("gemm: the mirrored epilogue needs lower_only, a square result, beta == 0 and no split-k / grouping");
     return GSCF_B200_ERR_INVALID_ARG;
   }
+  // GSCF_B200_GEMM_TMA: 0 = cp.async only, 1 = 1-D bulk copies for the NT products only, 2 (default) = also the
+  // tensor-map kernel for k-contiguous operands
   static int tma = -1;
-  if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] == '0') ? 0 : 1; }
+  if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] >= '0' && te[0] <= '2') ? te[0] - '0' : 2; }
   GemmParams p = pin;
   p.use_tma = tma;
   if (batch > 65535) {

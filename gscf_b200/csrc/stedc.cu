@@ -109,7 +109,7 @@ __global__ void dc_split_kernel(const double* __restrict__ d, const double* __re
 constexpr int kLeafWarps = 8;
 __global__ void __launch_bounds__(kLeafWarps * 32)
 dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws, double* __restrict__ Z0, int ldz,
-                    long long sZ, int nbatch, const int* __restrict__ map) {
+                    long long sZ, int nbatch, const int* __restrict__ map, int zs) {
   extern __shared__ __align__(16) double lsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long gl = (long long)blockIdx.x * kLeafWarps + warp;  // leaves of all matrices, flattened
@@ -118,12 +118,16 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
   const long long q = map ? map[zb] : zb;
   const int n = ws.n, L = ws.L;
   const int lo = bnd(leaf, n, L), hi = bnd(leaf + 1, n, L), m = hi - lo;
-  double* Zs = lsm + (size_t)warp * (kLeaf * kLeaf + 2 * kLeaf);  // Zs[col * 32 + row]
-  double* sd = Zs + kLeaf * kLeaf;
-  double* se = sd + kLeaf;
+  // zs >= m: column stride of the leaf's eigenvector block = the largest leaf order of this launch, so that the shared
+  // memory of a block follows the leaf size (leaves of 16: 18 KB instead of 70 KB per block - 8 instead of 3 blocks per SM;
+  // 512 matrices of order 128 are 512 blocks, which were 1.15 waves of 444 slots)
+  double* Zs = lsm + (size_t)warp * (zs * zs + 2 * zs);  // Zs[col * zs + row]
+  double* sd = Zs + zs * zs;
+  double* se = sd + zs;
   const double* dm = ws.dmod + q * n + lo;
   const double* eq = e + q * dstride + lo;
-  for (int c = 0; c < m; ++c) Zs[c * kLeaf + lane] = (c == lane) ? 1.0 : 0.0;
+  if (lane < m)
+    for (int c = 0; c < m; ++c) Zs[c * zs + lane] = (c == lane) ? 1.0 : 0.0;
   if (lane < m) {
     sd[lane] = dm[lane];
     se[lane] = lane < m - 1 ? eq[lane] : 0.0;
@@ -175,9 +179,9 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
         if (lane == 0) sd[i + 1] = g + p;
         g = cs * r - b;
         if (lane < m) {
-          const double z1 = Zs[(i + 1) * kLeaf + lane], z0 = Zs[i * kLeaf + lane];
-          Zs[(i + 1) * kLeaf + lane] = sn * z0 + cs * z1;
-          Zs[i * kLeaf + lane] = cs * z0 - sn * z1;
+          const double z1 = Zs[(i + 1) * zs + lane], z0 = Zs[i * zs + lane];
+          Zs[(i + 1) * zs + lane] = sn * z0 + cs * z1;
+          Zs[i * zs + lane] = cs * z0 - sn * z1;
         }
         di1 = di; di = din; ei = ein;
       }
@@ -192,7 +196,7 @@ dc_leaf_tql2_kernel(const double* __restrict__ e, long long dstride, StedcWs ws,
   double* Zq = Z0 + q * sZ;
   double* lam = ws.lam[0] + q * n;
   for (int c = 0; c < m; ++c)
-    if (lane < m) Zq[(size_t)(lo + c) * ldz + lo + lane] = Zs[c * kLeaf + lane];
+    if (lane < m) Zq[(size_t)(lo + c) * ldz + lo + lane] = Zs[c * zs + lane];
   if (lane < m) lam[lo + lane] = sd[lane];
 }
 
@@ -735,18 +739,23 @@ int stedc_batched(int n, double* d, double* e, long long dstride, double* w, lon
   dc_split_kernel<<<dim3(std::max(1, ceil_div(n, 256)), batch), 256, 0, st>>>(d, e, dstride, ws, map);
   count_launch(1);
   GSCF_CHECK_LAUNCH();
-  const size_t leaf_smem = (size_t)kLeafWarps * (kLeaf * kLeaf + 2 * kLeaf) * sizeof(double);
+  // GSCF_B200_DC_LEAF_SMEM=full: the 32-column layout whatever the leaf size (A/B)
+  static int leaf_full = -1;
+  if (leaf_full < 0) { const char* lf = getenv("GSCF_B200_DC_LEAF_SMEM"); leaf_full = (lf && lf[0] == 'f') ? 1 : 0; }
+  const int zs = leaf_full ? kLeaf : std::max(1, std::min(kLeaf, ws.lmax));
+  const size_t leaf_smem = (size_t)kLeafWarps * (zs * zs + 2 * zs) * sizeof(double);
+  const size_t leaf_smem_max = (size_t)kLeafWarps * (kLeaf * kLeaf + 2 * kLeaf) * sizeof(double);
   static PerDeviceOnce once;
   int dev;
   const bool configure = once.need(dev);
   if (configure) {
-    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_leaf_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem));
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_leaf_tql2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem_max));
     GSCF_CUDA_TRY(cudaFuncSetAttribute(dc_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     once.done(dev);
   }
   zero_matrix_kernel<<<dim3(gx, batch), 256, 0, st>>>(bufp[cur], bufld[cur], bufs[cur], n, map);
   dc_leaf_tql2_kernel<<<(unsigned)ceil_div_ll((long long)ws.nleaf * batch, kLeafWarps), kLeafWarps * 32, leaf_smem, st>>>(
-      e, dstride, ws, bufp[cur], bufld[cur], bufs[cur], batch, map);
+      e, dstride, ws, bufp[cur], bufld[cur], bufs[cur], batch, map, zs);
   count_launch(2);
   GSCF_CHECK_LAUNCH();
   int lev = 0;

@@ -70,6 +70,7 @@ SIGNATURES = {
     "gscf_b200_last_error": (C.c_char_p, []),
     "gscf_b200_version_string": (C.c_char_p, []),
     "gscf_b200_launch_count": (C.c_uint64, []),
+    "gscf_b200_tensor_map_launch_count": (C.c_uint64, []),
     "gscf_b200_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _P, C.c_int, _LL,
                                   _P, C.c_int, _LL, C.c_double, _P, C.c_int, _LL, C.c_int, _P]),
     "gscf_b200_syev_worksize": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

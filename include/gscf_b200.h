@@ -61,6 +61,9 @@ const char* gscf_b200_last_error(void);
 const char* gscf_b200_version_string(void);
 /* Number of CUDA kernels launched by this library since process start (bench.py: gpu_launches). */
 uint64_t gscf_b200_launch_count(void);
+/* How many of those were GEMM launches whose k-contiguous operand(s) went through tensor-map TMA
+ * (cp.async.bulk.tensor); tests use it to prove that path ran.  GSCF_B200_GEMM_TMA=1 keeps it at zero. */
+uint64_t gscf_b200_tensor_map_launch_count(void);
 
 /* ======================================================================================
  * 1. Building blocks on raw device pointers (stream = cudaStream_t passed as void*)

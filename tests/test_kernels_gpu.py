@@ -77,6 +77,51 @@ def test_dgemm_batched_and_large_tile(env):
         assert np.abs(got[b] - ref).max() < 1e-11
 
 
+@pytest.mark.parametrize("ta,tb,m,n,k,batch", [
+    (0, 0, 256, 200, 96, 1),       # NN, 64 x 64 tiles: A by 1-D bulk copies, B through its tensor map, ragged n
+    (1, 0, 257, 300, 130, 1),      # TN: both operands through tensor maps, ragged m / n / k (zero fill by the TMA unit)
+    (1, 1, 190, 192, 64, 3),       # TT, strided batch: A through its map (third coordinate = batch entry), B bulk
+    (0, 0, 1536, 1408, 160, 2),    # NN, 128 x 128 tiles
+    (1, 0, 1024, 1024, 100, 2),    # TN, 128 x 128 tiles, k not a multiple of the k-tile
+    (1, 0, 64, 1024, 1024, 1),     # TN, short and wide (V^T Z of the back-transformation)
+])
+def test_dgemm_tensor_map_path(env, ta, tb, m, n, k, batch):
+    """k-contiguous operands staged by tensor-map TMA (cp.async.bulk.tensor, `dgemm_dmma_tm_kernel`): result against numpy and
+    proof that the path ran (the launch counter of that kernel moves)."""
+    import os
+
+    torch, L = env
+    if os.environ.get("GSCF_B200_GEMM_TMA", "2") != "2":
+        pytest.skip("tensor-map path switched off by GSCF_B200_GEMM_TMA")
+    rng = np.random.default_rng(m + 3 * n + 7 * k + ta + 2 * tb)
+    ra, ca = (k, m) if ta else (m, k)
+    rb, cb = (n, k) if tb else (k, n)
+    lda, ldb, ldc = ra + (ra % 2) + 2, rb + (rb % 2), m + 1   # even leading dimensions: 16-byte aligned columns
+    sA, sB, sC = lda * ca + 4, ldb * cb, ldc * n
+    A = rng.standard_normal((batch, ra, ca))
+    B = rng.standard_normal((batch, rb, cb))
+    Cm = rng.standard_normal((batch, m, n))
+    bufA, bufB, bufC = np.zeros(batch * sA), np.zeros(batch * sB), np.zeros(batch * sC)
+    for b in range(batch):
+        bufA[b * sA: b * sA + lda * ca] = colmajor(A[b], lda)
+        bufB[b * sB: b * sB + ldb * cb] = colmajor(B[b], ldb)
+        bufC[b * sC: b * sC + ldc * n] = colmajor(Cm[b], ldc)
+    dA, dB, dC = dev(torch, bufA), dev(torch, bufB), dev(torch, bufC)
+    alpha, beta = -0.75, 0.5
+    before = L.lib.gscf_b200_tensor_map_launch_count()
+    L.check(L.lib.gscf_b200_dgemm(ta, tb, m, n, k, alpha, dA.data_ptr(), lda, sA, dB.data_ptr(), ldb, sB, beta,
+                                  dC.data_ptr(), ldc, sC, batch, None))
+    torch.cuda.synchronize()
+    assert L.lib.gscf_b200_tensor_map_launch_count() == before + 1, "the tensor-map kernel did not run"
+    got = dC.cpu().numpy()
+    for b in range(batch):
+        opA = A[b].T if ta else A[b]
+        opB = B[b].T if tb else B[b]
+        ref = alpha * (opA @ opB) + beta * Cm[b]
+        gb = from_colmajor(got[b * sC: b * sC + ldc * n], m, n, ldc)
+        assert np.abs(gb - ref).max() < 1e-13 * max(1, k) * (1 + np.abs(ref).max())
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 14, 31, 32, 33, 64, 100, 128, 160])
 def test_syev_jacobi(env, n):
     torch, L = env
