@@ -28,7 +28,9 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 uint64_t launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
 
-template <int BM, int BN, int BK, bool TA, bool TB, bool TM = false>
+// TM: 0 = cp.async / 1-D bulk copies, 1 = tensor maps for the k-contiguous operands (the other operand by bulk copies),
+// 2 = tensor maps for both operand layouts
+template <int BM, int BN, int BK, bool TA, bool TB, int TM = 0>
 struct SmemLayout {
   static constexpr int A_CE = TA ? BK : BM;  // contiguous extent
   static constexpr int A_SE = TA ? BM : BK;  // strided extent
@@ -36,13 +38,16 @@ struct SmemLayout {
   static constexpr int B_SE = TB ? BK : BN;
   static constexpr int A_LD = A_CE + 4;
   static constexpr int B_LD = B_CE + 4;
-  // TM: a k-contiguous operand is staged by tensor-map TMA as s[k / 4][row][4] (dense)
-  static constexpr bool A_TM = TM && TA;
-  static constexpr bool B_TM = TM && !TB;
-  static constexpr int A_ELEMS = A_TM ? BM * BK : A_SE * A_LD;
-  static constexpr int B_ELEMS = B_TM ? BN * BK : B_SE * B_LD;
+  // TM >= 1: a k-contiguous operand is staged by tensor-map TMA as s[k / 4][row][4] (dense);
+  // TM == 2: an m- / n-contiguous operand as s[row / 8][k][8] (dense) - see tma_tensor4d_g2s
+  static constexpr bool A_TM = TM >= 1 && TA;
+  static constexpr bool B_TM = TM >= 1 && !TB;
+  static constexpr bool A_MM = TM == 2 && !TA;
+  static constexpr bool B_MM = TM == 2 && TB;
+  static constexpr int A_ELEMS = (A_TM || A_MM) ? BM * BK : A_SE * A_LD;
+  static constexpr int B_ELEMS = (B_TM || B_MM) ? BN * BK : B_SE * B_LD;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-  static_assert(!TM || (A_ELEMS % 16 == 0 && B_ELEMS % 16 == 0), "TMA destinations stay 128-byte aligned");
+  static_assert(TM == 0 || (A_ELEMS % 16 == 0 && B_ELEMS % 16 == 0), "TMA destinations stay 128-byte aligned");
 };
 
 // One box of a 3-D tensor map -> shared memory, completing on `bar` (coordinates innermost first).
@@ -77,7 +82,20 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
   }
 }
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, bool TM>
+// One box of a 4-D tensor map.  Used for the m- / n-contiguous operands: the matrix (element (r, kk) at base[kk ld + r]) is
+// described as {8 rows, k, row groups of 8, batch entry} with strides {ld, 8 elements, batch stride}; a box of
+// 8 x BK x BM/8 lands as s[row group][k][8 rows], where the 32 lanes of a DMMA fragment (row = lane / 4, k = lane % 4) read
+// 32 consecutive doubles in permuted order - conflict-free without padding, one TMA instruction per operand and stage.
+__device__ __forceinline__ void tma_tensor4d_g2s(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                                 uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, int TM>
 __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUtensorMap* tmA, const CUtensorMap* tmB) {
   using L = SmemLayout<BM, BN, BK, TA, TB, TM>;
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
@@ -167,8 +185,8 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
   // (18.8 vs 23.4 TFLOP/s), both through TMA faster (NT 4096^3: 30.0 vs 25.7 TFLOP/s).
   // TM kernel: the host has checked shapes and alignment of the whole launch - every CTA takes the TMA path, the
   // k-contiguous operand(s) through the tensor map(s), the other one through bulk copies
-  const bool both = TM || (interior && !TA && TB && alignedA && alignedB);
-  const bool bulkA = TM ? !TA : both, bulkB = TM ? TB : both;
+  const bool both = TM != 0 || (interior && !TA && TB && alignedA && alignedB);
+  const bool bulkA = TM == 2 ? false : TM == 1 ? !TA : both, bulkB = TM == 2 ? false : TM == 1 ? TB : both;
   const bool use_bulk = both;
   if (use_bulk) {
     if (threadIdx.x == 0) {
@@ -185,7 +203,7 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
     double* sB = sA + L::A_ELEMS;
     const double* Aq = A + (size_t)q * p.skA;
     const double* Bq = B + (size_t)q * p.skB;
-    const unsigned bytes = (unsigned)(((bulkA || TM ? BM : 0) + (bulkB || TM ? BN : 0)) * BK * sizeof(double));
+    const unsigned bytes = (unsigned)(((bulkA || TM != 0 ? BM : 0) + (bulkB || TM != 0 ? BN : 0)) * BK * sizeof(double));
     // warp 0 issues the bulk copies: expect_tx first, then one copy per tile row
     if (threadIdx.x < 32) {
       fence_proxy_async();  // generic-proxy reads of this stage (ordered by the barrier above) before the async-proxy writes
@@ -197,16 +215,19 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
       if (bulkB)
         for (int r = threadIdx.x; r < L::B_SE; r += 32)
           tma_bulk_g2s(sB + r * L::B_LD, Bq + (size_t)(k0 + r) * ldb + n0, (unsigned)(L::B_CE * sizeof(double)), &s_bar[stage]);
-      if (TM) {
+      if (TM != 0) {
         // one box of 4 (k) x BM / BN rows per k-group; rows and k beyond the matrix are zero-filled by the TMA unit and
         // still count as full boxes towards the expected bytes
         if (L::A_TM && threadIdx.x < BK / 4)
           tma_tensor3d_g2s(sA + threadIdx.x * (BM * 4), tmA, k0 + 4 * (int)threadIdx.x, m0, p.sA != 0 ? zq : 0, &s_bar[stage]);
         if (L::B_TM && threadIdx.x < BK / 4)
           tma_tensor3d_g2s(sB + threadIdx.x * (BN * 4), tmB, k0 + 4 * (int)threadIdx.x, n0, p.sB != 0 ? zq : 0, &s_bar[stage]);
+        // m- / n-contiguous operand: ONE box of 8 rows x BK x BM/8 row groups
+        if (L::A_MM && threadIdx.x == 0) tma_tensor4d_g2s(sA, tmA, 0, k0, m0 >> 3, p.sA != 0 ? zq : 0, &s_bar[stage]);
+        if (L::B_MM && threadIdx.x == 0) tma_tensor4d_g2s(sB, tmB, 0, k0, n0 >> 3, p.sB != 0 ? zq : 0, &s_bar[stage]);
       }
     }
-    if (TM) return;
+    if (TM != 0) return;
     // the other operand (k-contiguous rows) through cp.async
     if (!bulkA) {
       if (TA) {
@@ -264,12 +285,18 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         const int r = wm + i * 8 + lr;
-        af[i] = L::A_TM ? sA[((kk >> 2) * BM + r) * 4 + lc] : TA ? sA[r * L::A_LD + kk + lc] : sA[(kk + lc) * L::A_LD + r];
+        af[i] = L::A_TM   ? sA[((kk >> 2) * BM + r) * 4 + lc]
+                : L::A_MM ? sA[((((wm >> 3) + i) * BK) + kk + lc) * 8 + lr]
+                : TA      ? sA[r * L::A_LD + kk + lc]
+                          : sA[(kk + lc) * L::A_LD + r];
       }
 #pragma unroll
       for (int j = 0; j < NI; ++j) {
         const int c = wn + j * 8 + lr;
-        bf[j] = L::B_TM ? sB[((kk >> 2) * BN + c) * 4 + lc] : TB ? sB[(kk + lc) * L::B_LD + c] : sB[c * L::B_LD + kk + lc];
+        bf[j] = L::B_TM   ? sB[((kk >> 2) * BN + c) * 4 + lc]
+                : L::B_MM ? sB[((((wn >> 3) + j) * BK) + kk + lc) * 8 + lr]
+                : TB      ? sB[(kk + lc) * L::B_LD + c]
+                          : sB[c * L::B_LD + kk + lc];
       }
 #pragma unroll
       for (int i = 0; i < MI; ++i)
@@ -346,14 +373,14 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 dgemm_dmma_kernel(const GemmParams p) {
-  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, false>(p, nullptr, nullptr);
+  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, 0>(p, nullptr, nullptr);
 }
 
-// the same tiles with the k-contiguous operand(s) fed by tensor-map TMA (maps live in the kernel's parameter space)
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
+// the same tiles with operands fed by tensor-map TMA (maps live in the kernel's parameter space); TM as in SmemLayout
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, int TM>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 dgemm_dmma_tm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
-  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, true>(p, &tmA, &tmB);
+  dgemm_dmma_body<BM, BN, BK, WM, WN, STAGES, TA, TB, TM>(p, &tmA, &tmB);
 }
 
 // ---- host side of the tensor-map path ------------------------------------------------------------------------------
@@ -395,22 +422,80 @@ static bool encode_kmajor_map(CUtensorMap* tm, const double* base, int k, int ro
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// {8 rows, k, row groups of 8, batch entries} over an m- / n-contiguous operand (element (r, kk) at base[kk ld + r]);
+// box 8 x box_k x box_rows/8 x 1 (see tma_tensor4d_g2s).  The row-group stride (64 bytes) is smaller than the k stride.
+static bool encode_mmajor_map(CUtensorMap* tm, const double* base, int k, int rows, int ld, long long stride, int box_rows,
+                              int box_k, int entries) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t groups = (cuuint64_t)ceil_div(rows, 8);
+  const cuuint64_t dims[4] = {8, (cuuint64_t)k, groups, stride != 0 ? (cuuint64_t)entries : 1};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * sizeof(double), 8 * sizeof(double),
+                                 stride != 0 ? (cuuint64_t)stride * sizeof(double) : 64 * groups};
+  const cuuint32_t box[4] = {8, (cuuint32_t)box_k, (cuuint32_t)(box_rows / 8), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool aligned16(const void* ptr, int ld, long long stride) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld & 1) == 0 && (stride & 1) == 0;
 }
 
-// Does this launch qualify for the tensor-map kernel?  (Whole-launch decision: every CTA then takes the TMA path.)
-template <int BM, int BN, int BK, bool TA, bool TB>
+// Does this launch qualify for the tensor-map kernel of level TM?  (Whole-launch decision: every CTA then takes the TMA path.)
+template <int BM, int BN, int BK, bool TA, bool TB, int TM>
 static bool tm_eligible(const GemmParams& p) {
-  if (!(TA || !TB)) return false;                    // NT products have no k-contiguous operand: 1-D bulk copies
-  if (p.use_tma < 2 || p.descs != nullptr || p.kbatch != 1) return false;
+  if (TM == 1 && !(TA || !TB)) return false;         // level 1, NT products: no k-contiguous operand, 1-D bulk copies
+  if (p.descs != nullptr || p.kbatch != 1) return false;
   if (p.m <= 0 || p.n <= 0 || p.k <= 0) return false;
   if (!aligned16(p.A, p.lda, p.sA) || !aligned16(p.B, p.ldb, p.sB)) return false;
   if (p.sA < 0 || p.sB < 0 || p.sA >= (1LL << 36) || p.sB >= (1LL << 36)) return false;
-  // an operand staged by 1-D bulk copies has no zero fill: full tiles along its contiguous direction and along k
-  if (!TA && (p.m % BM != 0 || p.k % BK != 0)) return false;
-  if (TB && (p.n % BN != 0 || p.k % BK != 0)) return false;
+  if (TM == 1) {
+    // an operand staged by 1-D bulk copies has no zero fill: full tiles along its contiguous direction and along k
+    if (!TA && (p.m % BM != 0 || p.k % BK != 0)) return false;
+    if (TB && (p.n % BN != 0 || p.k % BK != 0)) return false;
+  } else {
+    // the 4-D map addresses whole groups of 8 rows: the last group must stay inside the column (ld >= rows rounded up;
+    // what it reads beyond the matrix only reaches rows of the product that are not stored)
+    if (!TA && p.lda < round_up(p.m, 8)) return false;
+    if (TB && p.ldb < round_up(p.n, 8)) return false;
+  }
   return true;
+}
+
+// Try the tensor-map kernel of level TM; `launched` tells whether it ran (false: not eligible or the driver refused a map)
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB, int TM>
+static int try_launch_tm(const GemmParams& p, int batch, dim3 grid, cudaStream_t st, bool& launched) {
+  constexpr int NT = (BM / WM) * (BN / WN) * 32;
+  launched = false;
+  if (!tm_eligible<BM, BN, BK, TA, TB, TM>(p)) return GSCF_B200_OK;
+  CUtensorMap tmA, tmB;
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmB, 0, sizeof(tmB));
+  bool ok = true;
+  // batch extent of the map: only bounds the zero fill; an index-mapped batch may address any problem of the engine
+  const int entries = p.batch_map ? 65536 : batch;
+  if (TA) ok = ok && encode_kmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, entries);
+  else if (TM == 2) ok = ok && encode_mmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, BK, entries);
+  if (!TB) ok = ok && encode_kmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, entries);
+  else if (TM == 2) ok = ok && encode_mmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, BK, entries);
+  if (!ok) return GSCF_B200_OK;
+  using L = SmemLayout<BM, BN, BK, TA, TB, TM>;
+  const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
+  auto kern = dgemm_dmma_tm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB, TM>;
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(dev)) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.done(dev);
+  }
+  kern<<<grid, NT, smem, st>>>(p, tmA, tmB);
+  count_launch();
+  g_tmap_launches.fetch_add(1, std::memory_order_relaxed);
+  GSCF_CHECK_LAUNCH();
+  launched = true;
+  return GSCF_B200_OK;
 }
 
 template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool TA, bool TB>
@@ -418,32 +503,17 @@ static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cuda
   constexpr int NT = (BM / WM) * (BN / WN) * 32;
   dim3 grid(ceil_div(max_m, BM), ceil_div(max_n, BN), batch);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return GSCF_B200_OK;
-  if constexpr (TA || !TB) {
-    if (tm_eligible<BM, BN, BK, TA, TB>(p)) {
-      CUtensorMap tmA, tmB;
-      memset(&tmA, 0, sizeof(tmA));
-      memset(&tmB, 0, sizeof(tmB));
-      bool ok = true;
-      // batch extent of the map: only bounds the zero fill; an index-mapped batch may address any problem of the engine
-      const int entries = p.batch_map ? 65536 : batch;
-      if (TA) ok = ok && encode_kmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, entries);
-      if (!TB) ok = ok && encode_kmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, entries);
-      if (ok) {
-        using L = SmemLayout<BM, BN, BK, TA, TB, true>;
-        const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
-        auto kern = dgemm_dmma_tm_kernel<BM, BN, BK, WM, WN, STAGES, TA, TB>;
-        static PerDeviceOnce once;
-        int dev;
-        if (once.need(dev)) {
-          GSCF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          once.done(dev);
-        }
-        kern<<<grid, NT, smem, st>>>(p, tmA, tmB);
-        count_launch();
-        g_tmap_launches.fetch_add(1, std::memory_order_relaxed);
-        GSCF_CHECK_LAUNCH();
-        return GSCF_B200_OK;
-      }
+  // Tensor-map kernels (levels of GSCF_B200_GEMM_TMA, see launch_gemm): measured on B200 they win on the 128 x 128 tiles
+  // (4096^3: NN 28.7 -> 30.6, TN 28.9 -> 31.9 TFLOP/s with level 2) and lose on the 64 x 64 tiles (1024^3 NN 22.9 -> 20.6)
+  bool launched = false;
+  if (p.use_tma >= 4 || (p.use_tma >= 3 && BM == 128)) {
+    GSCF_TRY((try_launch_tm<BM, BN, BK, WM, WN, STAGES, TA, TB, 2>(p, batch, grid, st, launched)));
+    if (launched) return GSCF_B200_OK;
+  }
+  if constexpr (BM == 128 && (TA || !TB)) {
+    if (p.use_tma >= 2) {
+      GSCF_TRY((try_launch_tm<BM, BN, BK, WM, WN, STAGES, TA, TB, 1>(p, batch, grid, st, launched)));
+      if (launched) return GSCF_B200_OK;
     }
   }
   using L = SmemLayout<BM, BN, BK, TA, TB>;
@@ -539,10 +609,11 @@ int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, i
     set_last_error("gemm: the mirrored epilogue needs lower_only, a square result, beta == 0 and no split-k / grouping");
     return GSCF_B200_ERR_INVALID_ARG;
   }
-  // GSCF_B200_GEMM_TMA: 0 = cp.async only, 1 = 1-D bulk copies for the NT products only, 2 (default) = also the
-  // tensor-map kernel for k-contiguous operands
+  // GSCF_B200_GEMM_TMA: 0 = cp.async only, 1 = 1-D bulk copies for the NT products only, 2 = also tensor maps for the
+  // k-contiguous operands of the 128 x 128 tiles, 3 (default) = tensor maps for both operand layouts on the 128 x 128
+  // tiles (falls back to 2 / 1 where a launch does not qualify), 4 = ... on the 64 x 64 tiles too
   static int tma = -1;
-  if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] >= '0' && te[0] <= '2') ? te[0] - '0' : 2; }
+  if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] >= '0' && te[0] <= '4') ? te[0] - '0' : 3; }
   GemmParams p = pin;
   p.use_tma = tma;
   if (batch > 65535) {

@@ -78,33 +78,36 @@ def test_dgemm_batched_and_large_tile(env):
 
 
 @pytest.mark.parametrize("ta,tb,m,n,k,batch", [
-    (0, 0, 256, 200, 96, 1),       # NN, 64 x 64 tiles: A by 1-D bulk copies, B through its tensor map, ragged n
-    (1, 0, 257, 300, 130, 1),      # TN: both operands through tensor maps, ragged m / n / k (zero fill by the TMA unit)
-    (1, 1, 190, 192, 64, 3),       # TT, strided batch: A through its map (third coordinate = batch entry), B bulk
-    (0, 0, 1536, 1408, 160, 2),    # NN, 128 x 128 tiles
-    (1, 0, 1024, 1024, 100, 2),    # TN, 128 x 128 tiles, k not a multiple of the k-tile
-    (1, 0, 64, 1024, 1024, 1),     # TN, short and wide (V^T Z of the back-transformation)
+    (0, 0, 1536, 1400, 160, 2),    # NN: A through the 4-D row-group map, B through its k-major map, ragged n
+    (1, 0, 1300, 1290, 130, 1),    # TN: both k-major, ragged m / n / k (zero fill by the TMA unit)
+    (1, 1, 1400, 1403, 64, 2),     # TT, strided batch (last map coordinate = batch entry), n not a multiple of 8
+    (0, 1, 1541, 1408, 100, 2),    # NT: both operands through 4-D row-group maps, ragged m, k not a multiple of the k-tile
+    (1, 0, 1024, 1024, 100, 2),    # TN, k not a multiple of the k-tile
+    (0, 1, 2048, 2048, 512, 1),    # NT, all tiles interior
 ])
 def test_dgemm_tensor_map_path(env, ta, tb, m, n, k, batch):
-    """k-contiguous operands staged by tensor-map TMA (cp.async.bulk.tensor, `dgemm_dmma_tm_kernel`): result against numpy and
-    proof that the path ran (the launch counter of that kernel moves)."""
+    """Operands staged by tensor-map TMA (cp.async.bulk.tensor, `dgemm_dmma_tm_kernel`; the 128 x 128 tile configuration):
+    result against numpy, NaN in every padding row (rows the maps may touch must not reach stored results), and proof
+    that the path ran (the launch counter of that kernel moves)."""
     import os
 
     torch, L = env
-    if os.environ.get("GSCF_B200_GEMM_TMA", "2") != "2":
+    if os.environ.get("GSCF_B200_GEMM_TMA", "3") not in ("3", "4"):
         pytest.skip("tensor-map path switched off by GSCF_B200_GEMM_TMA")
     rng = np.random.default_rng(m + 3 * n + 7 * k + ta + 2 * tb)
     ra, ca = (k, m) if ta else (m, k)
     rb, cb = (n, k) if tb else (k, n)
-    lda, ldb, ldc = ra + (ra % 2) + 2, rb + (rb % 2), m + 1   # even leading dimensions: 16-byte aligned columns
+    lda, ldb, ldc = (ra + 7) // 8 * 8 + 2, (rb + 7) // 8 * 8, m + 1   # even, >= rows rounded up to 8
     sA, sB, sC = lda * ca + 4, ldb * cb, ldc * n
     A = rng.standard_normal((batch, ra, ca))
     B = rng.standard_normal((batch, rb, cb))
     Cm = rng.standard_normal((batch, m, n))
-    bufA, bufB, bufC = np.zeros(batch * sA), np.zeros(batch * sB), np.zeros(batch * sC)
+    bufA, bufB, bufC = np.full(batch * sA, np.nan), np.full(batch * sB, np.nan), np.zeros(batch * sC)
     for b in range(batch):
-        bufA[b * sA: b * sA + lda * ca] = colmajor(A[b], lda)
-        bufB[b * sB: b * sB + ldb * cb] = colmajor(B[b], ldb)
+        va = bufA[b * sA: b * sA + lda * ca].reshape(ca, lda)
+        va[:, :ra] = A[b].T
+        vb = bufB[b * sB: b * sB + ldb * cb].reshape(cb, ldb)
+        vb[:, :rb] = B[b].T
         bufC[b * sC: b * sC + ldc * n] = colmajor(Cm[b], ldc)
     dA, dB, dC = dev(torch, bufA), dev(torch, bufB), dev(torch, bufC)
     alpha, beta = -0.75, 0.5
@@ -120,6 +123,21 @@ def test_dgemm_tensor_map_path(env, ta, tb, m, n, k, batch):
         ref = alpha * (opA @ opB) + beta * Cm[b]
         gb = from_colmajor(got[b * sC: b * sC + ldc * n], m, n, ldc)
         assert np.abs(gb - ref).max() < 1e-13 * max(1, k) * (1 + np.abs(ref).max())
+
+
+def test_dgemm_randomised_sweep_tensor_maps_on_small_tiles():
+    """The randomised GEMM sweep in a child process with GSCF_B200_GEMM_TMA=4: the tensor-map kernels also on the
+    64 x 64 tiles, where the default leaves them off (measured slower) - most shapes of the sweep use those tiles."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env2 = dict(os.environ, GSCF_B200_GEMM_TMA="4")
+    r = subprocess.run([sys.executable, "scripts/gemm_fuzz.py", "150", "900"], cwd=root, env=env2, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "failures 0" in r.stdout
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 14, 31, 32, 33, 64, 100, 128, 160])
