@@ -29,7 +29,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 uint64_t launch_count_value() { return g_launches.load(std::memory_order_relaxed); }
 
 // TM: 0 = cp.async / 1-D bulk copies, 1 = tensor maps for the k-contiguous operands (the other operand by bulk copies),
-// 2 = tensor maps for both operand layouts
+// 2 / 3 = tensor maps for both operand layouts, m- / n-contiguous operands in row groups of 8 / 4
 template <int BM, int BN, int BK, bool TA, bool TB, int TM = 0>
 struct SmemLayout {
   static constexpr int A_CE = TA ? BK : BM;  // contiguous extent
@@ -39,11 +39,12 @@ struct SmemLayout {
   static constexpr int A_LD = A_CE + 4;
   static constexpr int B_LD = B_CE + 4;
   // TM >= 1: a k-contiguous operand is staged by tensor-map TMA as s[k / 4][row][4] (dense);
-  // TM == 2: an m- / n-contiguous operand as s[row / 8][k][8] (dense) - see tma_tensor4d_g2s
+  // TM >= 2: an m- / n-contiguous operand as s[row / RG][k][RG] (dense) - see tma_tensor4d_g2s
+  static constexpr int RG = TM == 2 ? 8 : 4;
   static constexpr bool A_TM = TM >= 1 && TA;
   static constexpr bool B_TM = TM >= 1 && !TB;
-  static constexpr bool A_MM = TM == 2 && !TA;
-  static constexpr bool B_MM = TM == 2 && TB;
+  static constexpr bool A_MM = TM >= 2 && !TA;
+  static constexpr bool B_MM = TM >= 2 && TB;
   static constexpr int A_ELEMS = (A_TM || A_MM) ? BM * BK : A_SE * A_LD;
   static constexpr int B_ELEMS = (B_TM || B_MM) ? BN * BK : B_SE * B_LD;
   static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
@@ -83,9 +84,12 @@ __device__ __forceinline__ void load_operand(double* __restrict__ s, const doubl
 }
 
 // One box of a 4-D tensor map.  Used for the m- / n-contiguous operands: the matrix (element (r, kk) at base[kk ld + r]) is
-// described as {8 rows, k, row groups of 8, batch entry} with strides {ld, 8 elements, batch stride}; a box of
-// 8 x BK x BM/8 lands as s[row group][k][8 rows], where the 32 lanes of a DMMA fragment (row = lane / 4, k = lane % 4) read
-// 32 consecutive doubles in permuted order - conflict-free without padding, one TMA instruction per operand and stage.
+// described as {RG rows, k, row groups of RG, batch entry} with strides {ld, RG elements, batch stride}; a box of
+// RG x BK x BM/RG lands as s[row group][k][RG rows] - dense, one TMA instruction per operand and stage.  A DMMA fragment
+// (row = lane / 4, k = lane % 4) then reads, with RG = 4, 16 consecutive doubles per half-warp (lanes 0..15: rows 0..3 of one
+// group, lanes 16..31: the next group) - conflict-free.  RG = 8 was measured first (`profiles/r02_ncu_full_gemm_tm.json`:
+// NT 4096^3 32.1 TFLOP/s with 2.0e8 shared-memory bank conflicts per launch - the half-warp's 4 k x 4 rows fall on
+// 8 k-strided doubles twice - against 234 conflicts for the k-major maps).
 __device__ __forceinline__ void tma_tensor4d_g2s(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
                                                  uint64_t* bar) {
   asm volatile(
@@ -186,7 +190,7 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
   // TM kernel: the host has checked shapes and alignment of the whole launch - every CTA takes the TMA path, the
   // k-contiguous operand(s) through the tensor map(s), the other one through bulk copies
   const bool both = TM != 0 || (interior && !TA && TB && alignedA && alignedB);
-  const bool bulkA = TM == 2 ? false : TM == 1 ? !TA : both, bulkB = TM == 2 ? false : TM == 1 ? TB : both;
+  const bool bulkA = TM >= 2 ? false : TM == 1 ? !TA : both, bulkB = TM >= 2 ? false : TM == 1 ? TB : both;
   const bool use_bulk = both;
   if (use_bulk) {
     if (threadIdx.x == 0) {
@@ -222,9 +226,9 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
           tma_tensor3d_g2s(sA + threadIdx.x * (BM * 4), tmA, k0 + 4 * (int)threadIdx.x, m0, p.sA != 0 ? zq : 0, &s_bar[stage]);
         if (L::B_TM && threadIdx.x < BK / 4)
           tma_tensor3d_g2s(sB + threadIdx.x * (BN * 4), tmB, k0 + 4 * (int)threadIdx.x, n0, p.sB != 0 ? zq : 0, &s_bar[stage]);
-        // m- / n-contiguous operand: ONE box of 8 rows x BK x BM/8 row groups
-        if (L::A_MM && threadIdx.x == 0) tma_tensor4d_g2s(sA, tmA, 0, k0, m0 >> 3, p.sA != 0 ? zq : 0, &s_bar[stage]);
-        if (L::B_MM && threadIdx.x == 0) tma_tensor4d_g2s(sB, tmB, 0, k0, n0 >> 3, p.sB != 0 ? zq : 0, &s_bar[stage]);
+        // m- / n-contiguous operand: ONE box of RG rows x BK x BM/RG row groups
+        if (L::A_MM && threadIdx.x == 0) tma_tensor4d_g2s(sA, tmA, 0, k0, m0 / L::RG, p.sA != 0 ? zq : 0, &s_bar[stage]);
+        if (L::B_MM && threadIdx.x == 0) tma_tensor4d_g2s(sB, tmB, 0, k0, n0 / L::RG, p.sB != 0 ? zq : 0, &s_bar[stage]);
       }
     }
     if (TM != 0) return;
@@ -286,7 +290,7 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
       for (int i = 0; i < MI; ++i) {
         const int r = wm + i * 8 + lr;
         af[i] = L::A_TM   ? sA[((kk >> 2) * BM + r) * 4 + lc]
-                : L::A_MM ? sA[((((wm >> 3) + i) * BK) + kk + lc) * 8 + lr]
+                : L::A_MM ? sA[(((wm + i * 8 + lr) / L::RG) * BK + kk + lc) * L::RG + (lr & (L::RG - 1))]
                 : TA      ? sA[r * L::A_LD + kk + lc]
                           : sA[(kk + lc) * L::A_LD + r];
       }
@@ -294,7 +298,7 @@ __device__ __forceinline__ void dgemm_dmma_body(const GemmParams& p, const CUten
       for (int j = 0; j < NI; ++j) {
         const int c = wn + j * 8 + lr;
         bf[j] = L::B_TM   ? sB[((kk >> 2) * BN + c) * 4 + lc]
-                : L::B_MM ? sB[((((wn >> 3) + j) * BK) + kk + lc) * 8 + lr]
+                : L::B_MM ? sB[(((wn + j * 8 + lr) / L::RG) * BK + kk + lc) * L::RG + (lr & (L::RG - 1))]
                 : TB      ? sB[(kk + lc) * L::B_LD + c]
                           : sB[c * L::B_LD + kk + lc];
       }
@@ -422,17 +426,17 @@ static bool encode_kmajor_map(CUtensorMap* tm, const double* base, int k, int ro
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// {8 rows, k, row groups of 8, batch entries} over an m- / n-contiguous operand (element (r, kk) at base[kk ld + r]);
-// box 8 x box_k x box_rows/8 x 1 (see tma_tensor4d_g2s).  The row-group stride (64 bytes) is smaller than the k stride.
+// {rg rows, k, row groups of rg, batch entries} over an m- / n-contiguous operand (element (r, kk) at base[kk ld + r]);
+// box rg x box_k x box_rows/rg x 1 (see tma_tensor4d_g2s).  The row-group stride (rg doubles) is smaller than the k stride.
 static bool encode_mmajor_map(CUtensorMap* tm, const double* base, int k, int rows, int ld, long long stride, int box_rows,
-                              int box_k, int entries) {
+                              int box_k, int entries, int rg) {
   TmapEncodeFn enc = tmap_encode_fn();
   if (!enc) return false;
-  const cuuint64_t groups = (cuuint64_t)ceil_div(rows, 8);
-  const cuuint64_t dims[4] = {8, (cuuint64_t)k, groups, stride != 0 ? (cuuint64_t)entries : 1};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * sizeof(double), 8 * sizeof(double),
+  const cuuint64_t groups = (cuuint64_t)ceil_div(rows, rg);
+  const cuuint64_t dims[4] = {(cuuint64_t)rg, (cuuint64_t)k, groups, stride != 0 ? (cuuint64_t)entries : 1};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)rg * sizeof(double),
                                  stride != 0 ? (cuuint64_t)stride * sizeof(double) : 64 * groups};
-  const cuuint32_t box[4] = {8, (cuuint32_t)box_k, (cuuint32_t)(box_rows / 8), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)rg, (cuuint32_t)box_k, (cuuint32_t)(box_rows / rg), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -456,10 +460,11 @@ static bool tm_eligible(const GemmParams& p) {
     if (!TA && (p.m % BM != 0 || p.k % BK != 0)) return false;
     if (TB && (p.n % BN != 0 || p.k % BK != 0)) return false;
   } else {
-    // the 4-D map addresses whole groups of 8 rows: the last group must stay inside the column (ld >= rows rounded up;
+    // the 4-D map addresses whole groups of RG rows: the last group must stay inside the column (ld >= rows rounded up;
     // what it reads beyond the matrix only reaches rows of the product that are not stored)
-    if (!TA && p.lda < round_up(p.m, 8)) return false;
-    if (TB && p.ldb < round_up(p.n, 8)) return false;
+    constexpr int RG = SmemLayout<BM, BN, BK, TA, TB, TM>::RG;
+    if (!TA && p.lda < round_up(p.m, RG)) return false;
+    if (TB && p.ldb < round_up(p.n, RG)) return false;
   }
   return true;
 }
@@ -477,9 +482,9 @@ static int try_launch_tm(const GemmParams& p, int batch, dim3 grid, cudaStream_t
   // batch extent of the map: only bounds the zero fill; an index-mapped batch may address any problem of the engine
   const int entries = p.batch_map ? 65536 : batch;
   if (TA) ok = ok && encode_kmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, entries);
-  else if (TM == 2) ok = ok && encode_mmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, BK, entries);
+  else if (TM >= 2) ok = ok && encode_mmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, BK, entries, SmemLayout<BM, BN, BK, TA, TB, TM>::RG);
   if (!TB) ok = ok && encode_kmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, entries);
-  else if (TM == 2) ok = ok && encode_mmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, BK, entries);
+  else if (TM >= 2) ok = ok && encode_mmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, BK, entries, SmemLayout<BM, BN, BK, TA, TB, TM>::RG);
   if (!ok) return GSCF_B200_OK;
   using L = SmemLayout<BM, BN, BK, TA, TB, TM>;
   const size_t smem = (size_t)STAGES * L::STAGE_ELEMS * sizeof(double);
@@ -506,8 +511,15 @@ static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cuda
   // Tensor-map kernels (levels of GSCF_B200_GEMM_TMA, see launch_gemm): measured on B200 they win on the 128 x 128 tiles
   // (4096^3: NN 28.7 -> 30.6, TN 28.9 -> 31.9 TFLOP/s with level 2) and lose on the 64 x 64 tiles (1024^3 NN 22.9 -> 20.6)
   bool launched = false;
-  if (p.use_tma >= 4 || (p.use_tma >= 3 && BM == 128)) {
-    GSCF_TRY((try_launch_tm<BM, BN, BK, WM, WN, STAGES, TA, TB, 2>(p, batch, grid, st, launched)));
+  // ... with maps for both layouts (level 3) every product gains on the 128 x 128 tiles (4096^3: NN 32.0, NT 32.1, TN 31.9
+  // TFLOP/s) and the NT products also on the 64 x 64 tiles (1024 x 1024 x 128: 11.9 -> 14.6); the k-major maps (32-byte box
+  // rows, four boxes per operand and stage) stay off there (64 x 4096 x 4096 TN: 7.7 -> 7.5)
+  if (p.use_tma >= 4 || (p.use_tma >= 3 && (BM == 128 || (!TA && TB)))) {
+    // GSCF_B200_GEMM_RG=8: row groups of 8 in the 4-D maps (A/B; the default 4 is free of bank conflicts)
+    static int rg = -1;
+    if (rg < 0) { const char* re = getenv("GSCF_B200_GEMM_RG"); rg = (re && atoi(re) == 8) ? 8 : 4; }
+    if (rg == 8) GSCF_TRY((try_launch_tm<BM, BN, BK, WM, WN, STAGES, TA, TB, 2>(p, batch, grid, st, launched)));
+    else GSCF_TRY((try_launch_tm<BM, BN, BK, WM, WN, STAGES, TA, TB, 3>(p, batch, grid, st, launched)));
     if (launched) return GSCF_B200_OK;
   }
   if constexpr (BM == 128 && (TA || !TB)) {
@@ -611,7 +623,8 @@ int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, i
   }
   // GSCF_B200_GEMM_TMA: 0 = cp.async only, 1 = 1-D bulk copies for the NT products only, 2 = also tensor maps for the
   // k-contiguous operands of the 128 x 128 tiles, 3 (default) = tensor maps for both operand layouts on the 128 x 128
-  // tiles (falls back to 2 / 1 where a launch does not qualify), 4 = ... on the 64 x 64 tiles too
+  // tiles and for the NT products on the 64 x 64 tiles (falls back to 2 / 1 where a launch does not qualify), 4 = every
+  // product on the 64 x 64 tiles too
   static int tma = -1;
   if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] >= '0' && te[0] <= '4') ? te[0] - '0' : 3; }
   GemmParams p = pin;
