@@ -235,14 +235,19 @@ def run_reference(args, w):
 # ---------------------------------------------------------------------------------------------
 def ncu_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-    `ncu --set full` capture of the same kernel at this order (profiles/r01_ncu_full_trd_fused.json), else None."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_trd_fused.json")
-    try:
-        with open(path) as f:
-            rec = json.load(f)
-        return rec.get(str(n), {}).get("dram_bytes")
-    except (OSError, ValueError):
-        return None
+    `ncu --set full` capture of the same kernel at this order (round 2: profiles/r02_ncu_full_trd_{rega,blocked}.json,
+    else round 1: profiles/r01_ncu_full_trd_fused.json), else None."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    for name in ("r02_ncu_full_trd_rega.json", "r02_ncu_full_trd_blocked.json", "r01_ncu_full_trd_fused.json"):
+        try:
+            with open(os.path.join(here, name)) as f:
+                rec = json.load(f)
+        except (OSError, ValueError):
+            continue
+        got = rec.get(str(n), {}).get("dram_bytes")
+        if got is not None:
+            return got
+    return None
 
 
 class Job:

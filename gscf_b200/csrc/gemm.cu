@@ -511,10 +511,12 @@ static int launch_cfg(const GemmParams& p, int batch, int max_m, int max_n, cuda
   // Tensor-map kernels (levels of GSCF_B200_GEMM_TMA, see launch_gemm): measured on B200 they win on the 128 x 128 tiles
   // (4096^3: NN 28.7 -> 30.6, TN 28.9 -> 31.9 TFLOP/s with level 2) and lose on the 64 x 64 tiles (1024^3 NN 22.9 -> 20.6)
   bool launched = false;
-  // ... with maps for both layouts (level 3) every product gains on the 128 x 128 tiles (4096^3: NN 32.0, NT 32.1, TN 31.9
-  // TFLOP/s) and the NT products also on the 64 x 64 tiles (1024 x 1024 x 128: 11.9 -> 14.6); the k-major maps (32-byte box
-  // rows, four boxes per operand and stage) stay off there (64 x 4096 x 4096 TN: 7.7 -> 7.5)
-  if (p.use_tma >= 4 || (p.use_tma >= 3 && (BM == 128 || (!TA && TB)))) {
+  // ... with maps for both layouts (level 3) every product gains on the 128 x 128 tiles (4096^3: NN 31.6, NT 32.2, TN 31.9
+  // TFLOP/s, DMMA sub-pipe 86 - 88 % active) and on the 64 x 64 tiles all but the TN products, whose two k-major maps (32-byte
+  // box rows, four boxes per operand and stage) measured slower there (64 x 4096 x 4096 split-k TN: 7.7 -> 7.5; against
+  // 1024 x 1024 x 128 NT: 11.9 -> 14.4; whole SCF paths with / without the small-tile kernels: C2 190.0 / 188.9 it/s,
+  // C4 204.8 / 202.7 k it/s)
+  if (p.use_tma >= 4 || (p.use_tma >= 3 && (BM == 128 || !(TA && !TB)))) {
     // GSCF_B200_GEMM_RG=8: row groups of 8 in the 4-D maps (A/B; the default 4 is free of bank conflicts)
     static int rg = -1;
     if (rg < 0) { const char* re = getenv("GSCF_B200_GEMM_RG"); rg = (re && atoi(re) == 8) ? 8 : 4; }
@@ -623,8 +625,8 @@ int launch_gemm(bool ta, bool tb, const GemmParams& pin, int batch, int max_m, i
   }
   // GSCF_B200_GEMM_TMA: 0 = cp.async only, 1 = 1-D bulk copies for the NT products only, 2 = also tensor maps for the
   // k-contiguous operands of the 128 x 128 tiles, 3 (default) = tensor maps for both operand layouts on the 128 x 128
-  // tiles and for the NT products on the 64 x 64 tiles (falls back to 2 / 1 where a launch does not qualify), 4 = every
-  // product on the 64 x 64 tiles too
+  // tiles and, except for the TN products, on the 64 x 64 tiles (falls back to 2 / 1 where a launch does not qualify),
+  // 4 = every product on the 64 x 64 tiles too
   static int tma = -1;
   if (tma < 0) { const char* te = getenv("GSCF_B200_GEMM_TMA"); tma = (te && te[0] >= '0' && te[0] <= '4') ? te[0] - '0' : 3; }
   GemmParams p = pin;
