@@ -469,8 +469,20 @@ def measure(job, w, steps, warmup, cpu_baseline=True, sample_clocks=False, probl
             ach = per_launch / avg_s / 1e9
             sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
             mats_in_flight = max(1, min(P_local * nblk, 148))
-            roofline = {"kernel": "trd_fused_kernel (one-launch Householder tridiagonalisation: rank-2 update fused "
-                                  "with the trailing-matrix product, one L2 exchange per column)", "bound": "hbm",
+            if n <= 128:
+                kname = ("trd_solo_reg_kernel<128> / <64> (single-CTA Householder tridiagonalisation, the matrix in "
+                         "registers, one CTA per matrix of the batch; the trailing 64 x 64 block in a second launch)")
+            elif P_local * nblk > 2:
+                kname = ("trd_fused_kernel, symmetric-half variant (one cluster of 4 CTAs per matrix working in L2, two "
+                         "CTAs per SM; rank-2 update fused with the trailing-matrix product on the lower triangle)")
+            elif n > 1664 + 128:
+                kname = ("trd_fused_blocked_kernel -> trd_fused_kernel (one-launch Householder tridiagonalisation on all "
+                         "SMs: deferred updates while the trailing matrix exceeds L2, then in place in L2, then in shared "
+                         "memory; one or two L2 exchanges per column)")
+            else:
+                kname = ("trd_fused_kernel (one-launch Householder tridiagonalisation: rank-2 update fused "
+                         "with the trailing-matrix product, one L2 exchange per column)")
+            roofline = {"kernel": kname, "bound": "hbm",
                         "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                         "traffic": ncu_traffic(n),
                         "peak_source": peak_src, "avg_launch_ms": avg_s * 1e3, "launches_per_solve": launches_k,
