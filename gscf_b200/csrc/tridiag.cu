@@ -1015,6 +1015,109 @@ int back_transform(int n, const TrdWs& ws, double* Z, int ldz, long long sZ, int
   return GSCF_B200_OK;
 }
 
+
+// ---- back-transformation of small matrices (n <= 128: the C4 ensemble) ------------------------------------------------
+// The blocked route above costs a batch of small matrices ten launches (V, V^T V, T, W = V T on the side stream, then two
+// GEMMs per block of 64 reflectors), each of which streams the whole batch through HBM once or twice (4096 x 128 KB = 0.5 GB
+// per operand, far beyond L2): measured 2.1 ms for the four GEMMs + 1.6 ms of set-up per eigensolve of 4096 matrices, the
+// GEMMs at 9 - 20 TFLOP/s (`profiles/r02_ncu_sequence_eig_n128.txt`).  Here ONE CTA per matrix applies the reflectors one by
+// one (LAPACK dorm2r: Z <- H_0 (H_1 ( ... H_{n-2} Z))) with all reflectors in shared memory and Z in registers: the batch is
+// read once and written once, no T factors.  Thread (c = tid % 128, g = tid / 128) keeps rows 32 g .. 32 g + 31 of column c
+// of Z; a reflector costs one partial dot per thread, one barrier, four shared-memory reads and one update pass.  The
+// reflectors are stored with their explicit zeros and unit entry, so the passes need no row predicates; a row group that
+// lies entirely above the reflector skips both passes (uniform per warp).
+constexpr int BTS_T = 512;
+constexpr int BTS_NMAX = 128;
+inline size_t bts_smem_bytes(int n) {
+  const int np = round_up(n, 32);  // whole row groups: the passes read 32 rows without a bound check, the padding is zero
+  return ((size_t)n * np + n + 2 * 4 * BTS_NMAX) * sizeof(double);
+}
+__global__ void __launch_bounds__(BTS_T, 1)
+bt_small_kernel(const double* __restrict__ Ab, int lda, long long sA, const double* __restrict__ taub, int n,
+                double* __restrict__ Zb, int ldz, long long sZ, int nz, const int* __restrict__ map) {
+  extern __shared__ __align__(16) double bsm[];
+  const int np = (n + 31) & ~31;
+  double* sV = bsm;                          // [n][np]: column j = reflector j = [0 .. 0, 1, v_j, 0 ..], unit entry at row j + 1
+  double* stau = sV + (size_t)n * np;        // [n]
+  double* sred = stau + n;                   // [2][4][128] partial dots, double-buffered
+  const long long q = map ? map[blockIdx.x] : blockIdx.x;
+  const double* __restrict__ A = Ab + q * sA;
+  double* __restrict__ Z = Zb + q * sZ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid & (BTS_NMAX - 1), g = tid >> 7, r0 = 32 * g;
+  for (int j = warp; j < n; j += BTS_T / 32) {
+    const double* a = A + (size_t)j * lda;
+    for (int r = lane; r < np; r += 32)
+      sV[(size_t)j * np + r] = (j < n - 1 && r < n && r > j + 1) ? a[r] : ((j < n - 1 && r == j + 1) ? 1.0 : 0.0);
+  }
+  for (int j = tid; j < n; j += BTS_T) stau[j] = j < n - 1 ? (taub + q * n)[j] : 0.0;
+  double z[32];
+  const bool mine = c < nz;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[i] = (mine && r0 + i < n) ? Z[(size_t)c * ldz + r0 + i] : 0.0;
+  __syncthreads();
+  int buf = 0;
+  for (int j = n - 2; j >= 0; --j) {
+    const double tj = stau[j];
+    if (tj == 0.0) continue;  // H_j = I (uniform over the block)
+    const bool active = r0 + 31 >= j + 1 && r0 < n;  // my row group reaches below the reflector's leading zeros
+    const double2* v2 = reinterpret_cast<const double2*>(sV + (size_t)j * np + r0);
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const double2 a0 = v2[i / 2], a1 = v2[i / 2 + 1], a2 = v2[i / 2 + 2], a3 = v2[i / 2 + 3];
+        p0 = fma(a0.x, z[i], p0); p1 = fma(a0.y, z[i + 1], p1);
+        p2 = fma(a1.x, z[i + 2], p2); p3 = fma(a1.y, z[i + 3], p3);
+        p0 = fma(a2.x, z[i + 4], p0); p1 = fma(a2.y, z[i + 5], p1);
+        p2 = fma(a3.x, z[i + 6], p2); p3 = fma(a3.y, z[i + 7], p3);
+      }
+    }
+    double* red = sred + buf * (4 * BTS_NMAX);
+    red[g * BTS_NMAX + c] = (p0 + p1) + (p2 + p3);
+    __syncthreads();
+    buf ^= 1;
+    if (active) {
+      const double y = tj * ((red[c] + red[BTS_NMAX + c]) + (red[2 * BTS_NMAX + c] + red[3 * BTS_NMAX + c]));
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const double2 a = v2[i / 2];
+        z[i] = fma(-a.x, y, z[i]);
+        z[i + 1] = fma(-a.y, y, z[i + 1]);
+      }
+    }
+  }
+  if (mine) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (r0 + i < n) Z[(size_t)c * ldz + r0 + i] = z[i];
+  }
+}
+
+// n <= 128 and the switch GSCF_B200_BT_SMALL (default on)
+bool bt_small_route(int n) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GSCF_B200_BT_SMALL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on && n >= 2 && n <= BTS_NMAX;
+}
+
+int back_transform_small(int n, const double* A, int lda, long long sA, const TrdWs& ws, double* Z, int ldz, long long sZ,
+                         int batch, const int* map, cudaStream_t st, int nvec) {
+  const int nz = (nvec > 0 && nvec < n) ? nvec : n;
+  const size_t smem = bts_smem_bytes(n);
+  static PerDeviceOnce once;
+  int dev;
+  if (once.need(dev)) {
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(bt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bts_smem_bytes(BTS_NMAX)));
+    once.done(dev);
+  }
+  bt_small_kernel<<<batch, BTS_T, smem, st>>>(A, lda, sA, ws.tau, n, Z, ldz, sZ, nz, map);
+  count_launch();
+  GSCF_CHECK_LAUNCH();
+  return GSCF_B200_OK;
+}
+
 }  // namespace
 
 size_t tridiag_dc_worksize(int n, int batch) {
@@ -1074,6 +1177,17 @@ int tridiag_dc_syev_batched(int n, double* A, int lda, long long strideA, double
       cudaGetLastError();
       overlap = 0;
     }
+  }
+  const bool small_bt = bt_small_route(n);
+  if (small_bt) {
+    // one kernel after the D&C stage, nothing to prepare (see bt_small_kernel)
+    phase_mark(PH_STEDC, true, st);
+    GSCF_TRY(stedc_batched(n, ws.d, ws.e, n, w, stride_w, Z, ldz, strideZ, dws, batch, batch_map, info_dev, st, nvec));
+    phase_mark(PH_STEDC, false, st);
+    phase_mark(PH_BACKTRANSFORM, true, st);
+    GSCF_TRY(back_transform_small(n, A, lda, strideA, ws, Z, ldz, strideZ, batch, batch_map, st, nvec));
+    phase_mark(PH_BACKTRANSFORM, false, st);
+    return GSCF_B200_OK;
   }
   if (overlap) {
     GSCF_CUDA_TRY(cudaEventRecord(ev_fork, st));
