@@ -1028,57 +1028,110 @@ int back_transform(int n, const TrdWs& ws, double* Z, int ldz, long long sZ, int
 // lies entirely above the reflector skips both passes (uniform per warp).
 constexpr int BTS_T = 512;
 constexpr int BTS_NMAX = 128;
+// shared memory: reflectors [n][np] (the same region first / last stages Z for coalesced global accesses, column stride
+// n | 1), tau [n], s_j = v_{j-1}^T v_j [n], partial dots [2 buffers][2 reflectors][4 row groups][128 columns]
 inline size_t bts_smem_bytes(int n) {
   const int np = round_up(n, 32);  // whole row groups: the passes read 32 rows without a bound check, the padding is zero
-  return ((size_t)n * np + n + 2 * 4 * BTS_NMAX) * sizeof(double);
+  const size_t region = std::max((size_t)n * np, (size_t)n * (n | 1));
+  return (region + 2 * (size_t)n + 2 * 2 * 4 * BTS_NMAX) * sizeof(double);
 }
+// Two reflectors per barrier:  H_b H_a Z = Z - v_a y_a - v_b y_b  with  y_a = tau_a v_a^T Z,
+// y_b = tau_b (v_b^T Z - (v_b^T v_a) y_a): both partial dots come out of one pass over the thread's rows of Z, the scalar
+// products s = v_b^T v_a of consecutive reflectors are formed once up front (one warp per pair).
 __global__ void __launch_bounds__(BTS_T, 1)
 bt_small_kernel(const double* __restrict__ Ab, int lda, long long sA, const double* __restrict__ taub, int n,
                 double* __restrict__ Zb, int ldz, long long sZ, int nz, const int* __restrict__ map) {
   extern __shared__ __align__(16) double bsm[];
   const int np = (n + 31) & ~31;
+  const int zs = n | 1;                      // odd column stride of the staged Z: conflict-free for lanes along the columns
+  const size_t region = max((size_t)n * np, (size_t)n * zs);
   double* sV = bsm;                          // [n][np]: column j = reflector j = [0 .. 0, 1, v_j, 0 ..], unit entry at row j + 1
-  double* stau = sV + (size_t)n * np;        // [n]
-  double* sred = stau + n;                   // [2][4][128] partial dots, double-buffered
+  double* stau = sV + region;                // [n]
+  double* sdot = stau + n;                   // [n]: sdot[j] = v_{j-1}^T v_j
+  double* sred = sdot + n;                   // [2][2][4][128]
   const long long q = map ? map[blockIdx.x] : blockIdx.x;
   const double* __restrict__ A = Ab + q * sA;
   double* __restrict__ Z = Zb + q * sZ;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = BTS_T / 32;
   const int c = tid & (BTS_NMAX - 1), g = tid >> 7, r0 = 32 * g;
-  for (int j = warp; j < n; j += BTS_T / 32) {
+  const bool mine = c < nz;
+  // ---- Z: global -> shared (lanes along the rows) -> registers (lanes along the columns) ----------------------------
+  for (int col = warp; col < nz; col += NWARP)
+    for (int r = lane; r < n; r += 32) sV[(size_t)col * zs + r] = Z[(size_t)col * ldz + r];
+  __syncthreads();
+  double z[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) z[i] = (mine && r0 + i < n) ? sV[(size_t)c * zs + r0 + i] : 0.0;
+  __syncthreads();
+  // ---- reflectors -----------------------------------------------------------------------------------------------
+  for (int j = warp; j < n; j += NWARP) {
     const double* a = A + (size_t)j * lda;
     for (int r = lane; r < np; r += 32)
       sV[(size_t)j * np + r] = (j < n - 1 && r < n && r > j + 1) ? a[r] : ((j < n - 1 && r == j + 1) ? 1.0 : 0.0);
   }
   for (int j = tid; j < n; j += BTS_T) stau[j] = j < n - 1 ? (taub + q * n)[j] : 0.0;
-  double z[32];
-  const bool mine = c < nz;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) z[i] = (mine && r0 + i < n) ? Z[(size_t)c * ldz + r0 + i] : 0.0;
+  __syncthreads();
+  for (int j = 1 + warp; j < n - 1; j += NWARP) {
+    double sdt = 0.0;
+    for (int r = lane; r < np; r += 32) sdt = fma(sV[(size_t)(j - 1) * np + r], sV[(size_t)j * np + r], sdt);
+    sdt = warp_sum(sdt);
+    if (lane == 0) sdot[j] = sdt;
+  }
   __syncthreads();
   int buf = 0;
-  for (int j = n - 2; j >= 0; --j) {
-    const double tj = stau[j];
-    if (tj == 0.0) continue;  // H_j = I (uniform over the block)
-    const bool active = r0 + 31 >= j + 1 && r0 < n;  // my row group reaches below the reflector's leading zeros
-    const double2* v2 = reinterpret_cast<const double2*>(sV + (size_t)j * np + r0);
-    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+  int j = n - 2;
+  for (; j >= 1; j -= 2) {
+    // pair (a = j, b = j - 1): H_a first
+    const double ta = stau[j], tb = stau[j - 1];
+    const bool active = r0 + 31 >= j && r0 < n;  // my row group reaches below the leading zeros of reflector b
+    const double2* va = reinterpret_cast<const double2*>(sV + (size_t)j * np + r0);
+    const double2* vb = reinterpret_cast<const double2*>(sV + (size_t)(j - 1) * np + r0);
+    double pa0 = 0.0, pa1 = 0.0, pb0 = 0.0, pb1 = 0.0;
     if (active) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        const double2 a0 = v2[i / 2], a1 = v2[i / 2 + 1], a2 = v2[i / 2 + 2], a3 = v2[i / 2 + 3];
-        p0 = fma(a0.x, z[i], p0); p1 = fma(a0.y, z[i + 1], p1);
-        p2 = fma(a1.x, z[i + 2], p2); p3 = fma(a1.y, z[i + 3], p3);
-        p0 = fma(a2.x, z[i + 4], p0); p1 = fma(a2.y, z[i + 5], p1);
-        p2 = fma(a3.x, z[i + 6], p2); p3 = fma(a3.y, z[i + 7], p3);
+      for (int i = 0; i < 32; i += 4) {
+        const double2 a0 = va[i / 2], a1 = va[i / 2 + 1], b0 = vb[i / 2], b1 = vb[i / 2 + 1];
+        pa0 = fma(a0.x, z[i], pa0); pa1 = fma(a0.y, z[i + 1], pa1);
+        pb0 = fma(b0.x, z[i], pb0); pb1 = fma(b0.y, z[i + 1], pb1);
+        pa0 = fma(a1.x, z[i + 2], pa0); pa1 = fma(a1.y, z[i + 3], pa1);
+        pb0 = fma(b1.x, z[i + 2], pb0); pb1 = fma(b1.y, z[i + 3], pb1);
       }
     }
-    double* red = sred + buf * (4 * BTS_NMAX);
-    red[g * BTS_NMAX + c] = (p0 + p1) + (p2 + p3);
+    double* red = sred + buf * (2 * 4 * BTS_NMAX);
+    red[g * BTS_NMAX + c] = pa0 + pa1;
+    red[4 * BTS_NMAX + g * BTS_NMAX + c] = pb0 + pb1;
     __syncthreads();
     buf ^= 1;
     if (active) {
-      const double y = tj * ((red[c] + red[BTS_NMAX + c]) + (red[2 * BTS_NMAX + c] + red[3 * BTS_NMAX + c]));
+      const double ya = ta * ((red[c] + red[BTS_NMAX + c]) + (red[2 * BTS_NMAX + c] + red[3 * BTS_NMAX + c]));
+      const double* rb = red + 4 * BTS_NMAX;
+      const double yb = tb * (((rb[c] + rb[BTS_NMAX + c]) + (rb[2 * BTS_NMAX + c] + rb[3 * BTS_NMAX + c])) - sdot[j] * ya);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const double2 a = va[i / 2], b = vb[i / 2];
+        z[i] = fma(-b.x, yb, fma(-a.x, ya, z[i]));
+        z[i + 1] = fma(-b.y, yb, fma(-a.y, ya, z[i + 1]));
+      }
+    }
+  }
+  if (j == 0) {  // an even number of rows leaves reflector 0 alone
+    const double t0 = stau[0];
+    const bool active = r0 + 31 >= 1 && r0 < n;
+    const double2* v2 = reinterpret_cast<const double2*>(sV + r0);
+    double p0 = 0.0, p1 = 0.0;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const double2 a = v2[i / 2];
+        p0 = fma(a.x, z[i], p0); p1 = fma(a.y, z[i + 1], p1);
+      }
+    }
+    double* red = sred + buf * (2 * 4 * BTS_NMAX);
+    red[g * BTS_NMAX + c] = p0 + p1;
+    __syncthreads();
+    if (active) {
+      const double y = t0 * ((red[c] + red[BTS_NMAX + c]) + (red[2 * BTS_NMAX + c] + red[3 * BTS_NMAX + c]));
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const double2 a = v2[i / 2];
@@ -1087,11 +1140,16 @@ bt_small_kernel(const double* __restrict__ Ab, int lda, long long sA, const doub
       }
     }
   }
+  // ---- Z: registers -> shared -> global -------------------------------------------------------------------------
+  __syncthreads();  // every thread is done with the reflectors
   if (mine) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (r0 + i < n) Z[(size_t)c * ldz + r0 + i] = z[i];
+      if (r0 + i < n) sV[(size_t)c * zs + r0 + i] = z[i];
   }
+  __syncthreads();
+  for (int col = warp; col < nz; col += NWARP)
+    for (int r = lane; r < n; r += 32) Z[(size_t)col * ldz + r] = sV[(size_t)col * zs + r];
 }
 
 // n <= 128 and the switch GSCF_B200_BT_SMALL (default on)
