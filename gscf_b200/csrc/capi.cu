@@ -180,7 +180,7 @@ int gscf_b200_pulay_error(int n, int n_occ, double fac, const double* S, int lds
   a.F = F; a.ldf = ldf; a.sF = strideF;
   a.C = C; a.ldc = ldc; a.sC = strideC;
   a.E = E; a.lde = lde; a.sE = strideE;
-  a.work = work; a.swork = stride_work; a.batch = batch; a.batch_map = nullptr;
+  a.work = work; a.swork = stride_work; a.batch = batch; a.batch_map = nullptr; a.entries = 0;
   return pulay_error_fused(a, (cudaStream_t)stream);
 }
 

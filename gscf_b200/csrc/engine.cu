@@ -217,13 +217,13 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
     // T = Fd * X^T
     GemmParams g = gemm_params(n, n, n, 1.0, Fd + b * e->mstride, ld, e->X + (e->sx_stride ? b * e->mstride : 0), ld,
                                0.0, e->Tmp + b * e->mstride, ld);
-    g.sA = fd_pstride; g.sB = e->sx_stride ? e->pstride : 0; g.sC = e->pstride; g.batch_map = e->act_p;
+    g.sA = fd_pstride; g.sB = e->sx_stride ? e->pstride : 0; g.sC = e->pstride; g.batch_map = e->act_p; g.entries = e->P;
     g.ktri = tri ? 1 : 0;  // X^T(k, j) = X(j, k) = 0 for k > j
     GSCF_TRY(launch_gemm(false, tri, g, nact, n, n, e->stream));
     // A' = X * T
     GemmParams h = gemm_params(n, n, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Tmp + b * e->mstride, ld,
                                0.0, e->Aeig + b * e->mstride, ld);
-    h.sA = e->sx_stride ? e->pstride : 0; h.sB = e->pstride; h.sC = e->pstride; h.batch_map = e->act_p;
+    h.sA = e->sx_stride ? e->pstride : 0; h.sB = e->pstride; h.sC = e->pstride; h.batch_map = e->act_p; h.entries = e->P;
     h.ktri = tri ? 2 : 0;  // X(i, k) = 0 for k > i
     h.lower_only = tri ? 1 : 0;  // only the tiles on and below the diagonal are computed ...
     h.mirror = tri ? 1 : 0;      // ... and the epilogue stores every lower entry on both sides: A' exactly symmetric
@@ -235,7 +235,7 @@ int step_eigensolve(Engine* e, const double* Fd, long long fd_pstride, int nact)
   for (int b = 0; b < e->nblk; ++b) {
     GemmParams g = gemm_params(n, nv, n, 1.0, e->X + (e->sx_stride ? b * e->mstride : 0), ld, e->Zeig + b * e->mstride, ld,
                                0.0, e->Ccur() + b * e->mstride, ld);
-    g.sA = e->sx_stride ? e->pstride : 0; g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p;
+    g.sA = e->sx_stride ? e->pstride : 0; g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p; g.entries = e->P;
     g.ktri = tri ? 3 : 0;  // C = X^T Z:  X^T(i, k) = X(k, i) = 0 for k < i
     GSCF_TRY(launch_gemm(tri, false, g, nact, n, nv, e->stream));
   }
@@ -249,7 +249,7 @@ int step_density(Engine* e, int nact) {
   for (int b = 0; b < e->nblk; ++b) {
     GemmParams g = gemm_params(e->n, e->n, e->occ[b], 1.0, e->Ccur() + b * e->mstride, e->ld,
                                e->Ccur() + b * e->mstride, e->ld, 0.0, e->D + b * e->mstride, e->ld);
-    g.sA = g.sB = g.sC = e->pstride; g.batch_map = e->act_p;
+    g.sA = g.sB = g.sC = e->pstride; g.batch_map = e->act_p; g.entries = e->P;
     GSCF_TRY(launch_gemm(false, true, g, nact, e->n, e->n, e->stream));
   }
   return GSCF_B200_OK;
@@ -353,7 +353,7 @@ int step_error(Engine* e, int fslot, double* Edst, long long e_pstride, int nact
     a.C = e->Ccur() + b * e->mstride; a.ldc = ld; a.sC = e->pstride;
     a.E = Edst + b * e->mstride; a.lde = ld; a.sE = e_pstride;
     a.work = e->errwork + b * wstride; a.swork = e->nblk * wstride;
-    a.batch = nact; a.batch_map = e->act_p;
+    a.batch = nact; a.batch_map = e->act_p; a.entries = e->P;
     GSCF_TRY(pulay_error_fused(a, e->stream));
   }
   return GSCF_B200_OK;
@@ -1034,7 +1034,7 @@ int gscf_b200_solve_toda(gscf_b200_engine* e, const gscf_b200_params* prm) {
             const int o = e->occ[b];
             GemmParams g = gemm_params(n, o, n, 1.0, e->Fslot(PREV) + b * e->mstride, ld, e->Ccur() + b * e->mstride, ld,
                                        0.0, e->Tmp + b * e->mstride, ld);
-            g.sA = e->fring_pstride(); g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p;
+            g.sA = e->fring_pstride(); g.sB = e->pstride; g.sC = e->pstride; g.batch_map = e->act_p; g.entries = e->P;
             GSCF_TRY(launch_gemm(false, false, g, nact, n, o, e->stream));
             GSCF_TRY(multidot(e->Ccur() + b * e->mstride, e->pstride, e->Tmp + b * e->mstride, 0, e->pstride, self, n, o,
                               ld, nact, e->act_p, e->scal + b, 4, e->mdwork, e->stream));

@@ -388,6 +388,12 @@ dgemm_dmma_tm_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmA
 }
 
 // ---- host side of the tensor-map path ------------------------------------------------------------------------------
+static CUtensorMapL2promotion tmap_l2_promotion() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GSCF_B200_TMAP_L2"); v = e ? atoi(e) : 128; }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
 typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -422,7 +428,7 @@ static bool encode_kmajor_map(CUtensorMap* tm, const double* base, int k, int ro
   const cuuint32_t box[3] = {4, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tmap_l2_promotion(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -439,7 +445,7 @@ static bool encode_mmajor_map(CUtensorMap* tm, const double* base, int k, int ro
   const cuuint32_t box[4] = {(cuuint32_t)rg, (cuuint32_t)box_k, (cuuint32_t)(box_rows / rg), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, tmap_l2_promotion(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -455,6 +461,14 @@ static bool tm_eligible(const GemmParams& p) {
   if (p.m <= 0 || p.n <= 0 || p.k <= 0) return false;
   if (!aligned16(p.A, p.lda, p.sA) || !aligned16(p.B, p.ldb, p.sB)) return false;
   if (p.sA < 0 || p.sB < 0 || p.sA >= (1LL << 36) || p.sB >= (1LL << 36)) return false;
+  if (p.batch_map != nullptr && p.entries <= 0) return false;  // unknown batch extent (see try_launch_tm)
+  {
+    // no box larger than its tensor (GSCF_B200_TMAP_STRICT=0 lifts it): such products are too small to gain anything,
+    // and whole-box overhang is what the fault described in try_launch_tm needed
+    static int strict = -1;
+    if (strict < 0) { const char* e = getenv("GSCF_B200_TMAP_STRICT"); strict = e ? atoi(e) : 1; }
+    if (strict && (p.m < BM || p.n < BN || p.k < BK)) return false;
+  }
   if (TM == 1) {
     // an operand staged by 1-D bulk copies has no zero fill: full tiles along its contiguous direction and along k
     if (!TA && (p.m % BM != 0 || p.k % BK != 0)) return false;
@@ -480,7 +494,12 @@ static int try_launch_tm(const GemmParams& p, int batch, dim3 grid, cudaStream_t
   memset(&tmB, 0, sizeof(tmB));
   bool ok = true;
   // batch extent of the map: only bounds the zero fill; an index-mapped batch may address any problem of the engine
-  const int entries = p.batch_map ? 65536 : batch;
+  // Batch extent of the maps = the number of entries the operands really hold.  It must not be a loose bound: with an
+  // extent of 65536 (any index-mapped batch) a box reaching beyond the rows of a small matrix made the TMA unit touch
+  // memory behind the last problem - `Warp Illegal Address` in the 64 x 64 NT kernel, 24 problems of order 32, but only
+  // when the memory behind the engine's buffers was unmapped (found with cuda-gdb, gone with the exact extent; the rows
+  // concerned are never stored, so results were unaffected).
+  const int entries = p.batch_map ? p.entries : batch;
   if (TA) ok = ok && encode_kmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, entries);
   else if (TM >= 2) ok = ok && encode_mmajor_map(&tmA, p.A, p.k, p.m, p.lda, p.sA, BM, BK, entries, SmemLayout<BM, BN, BK, TA, TB, TM>::RG);
   if (!TB) ok = ok && encode_kmajor_map(&tmB, p.B, p.k, p.n, p.ldb, p.sB, BN, entries);
@@ -603,15 +622,15 @@ int pulay_error_fused(const PulayErrorArgs& a, cudaStream_t st) {
   double* W = a.work;                               // [S C_o | F C_o]
   double* W2 = a.work + (size_t)ldw * 2 * o;        // [F C_o | -S C_o]
   GemmParams g1 = gemm_params(n, o, n, 1.0, a.S, a.lds, a.C, a.ldc, 0.0, W, ldw);
-  g1.sA = a.sS; g1.sB = a.sC; g1.sC = a.swork; g1.batch_map = a.batch_map;
+  g1.sA = a.sS; g1.sB = a.sC; g1.sC = a.swork; g1.batch_map = a.batch_map; g1.entries = a.entries;
   g1.C2 = W2 + (size_t)ldw * o; g1.ldc2 = ldw; g1.sC2 = a.swork; g1.alpha2 = -1.0;
   GSCF_TRY(launch_gemm(false, false, g1, a.batch, n, o, st));
   GemmParams g2 = gemm_params(n, o, n, 1.0, a.F, a.ldf, a.C, a.ldc, 0.0, W + (size_t)ldw * o, ldw);
-  g2.sA = a.sF; g2.sB = a.sC; g2.sC = a.swork; g2.batch_map = a.batch_map;
+  g2.sA = a.sF; g2.sB = a.sC; g2.sC = a.swork; g2.batch_map = a.batch_map; g2.entries = a.entries;
   g2.C2 = W2; g2.ldc2 = ldw; g2.sC2 = a.swork; g2.alpha2 = 1.0;
   GSCF_TRY(launch_gemm(false, false, g2, a.batch, n, o, st));
   GemmParams g3 = gemm_params(n, n, 2 * o, a.fac, W, ldw, W2, ldw, 0.0, a.E, a.lde);
-  g3.sA = g3.sB = a.swork; g3.sC = a.sE; g3.batch_map = a.batch_map;
+  g3.sA = g3.sB = a.swork; g3.sC = a.sE; g3.batch_map = a.batch_map; g3.entries = a.entries;
   g3.lower_only = 1; g3.mirror = -1;
   return launch_gemm(false, true, g3, a.batch, n, n, st);
 }

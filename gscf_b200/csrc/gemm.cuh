@@ -31,6 +31,9 @@ struct GemmParams {
   long long skA, skB;     // strides between the q slices
   double alpha, beta;
   const int* batch_map;   // optional: batch entry z works on problem batch_map[z]
+  int entries;            // with batch_map: number of problems the operands hold (1 + the largest index the map may contain);
+                          // 0 = unknown, which keeps the launch off the tensor-map kernels (see gemm.cu: the batch extent of
+                          // a tensor map must not reach beyond the allocation)
   const GemmDesc* descs;  // optional: grouped mode, one descriptor per blockIdx.z
   int ktri;               // triangular operand: restrict the k range of every tile (kbatch == 1, no split-k)
                           //   1: k < n0 + BN   (op(B)(k, j) = 0 for k > j)      2: k < m0 + BM   (op(A)(i, k) = 0 for k > i)
@@ -54,7 +57,7 @@ inline GemmParams gemm_params(int m, int n, int k, double alpha, const double* A
   p.A = A; p.B = B; p.C = C; p.m = m; p.n = n; p.k = k;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.sA = p.sB = p.sC = 0; p.kbatch = 1; p.skA = p.skB = 0;
-  p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.descs = nullptr;
+  p.alpha = alpha; p.beta = beta; p.batch_map = nullptr; p.entries = 0; p.descs = nullptr;
   p.ksplit = 1; p.Cpart = nullptr; p.ktri = 0; p.lower_only = 0; p.use_tma = 0;
   p.mirror = 0; p.C2 = nullptr; p.ldc2 = 0; p.sC2 = 0; p.alpha2 = 0.0;
   return p;
@@ -100,6 +103,7 @@ struct PulayErrorArgs {
   double* work; long long swork;
   int batch;
   const int* batch_map;
+  int entries;            // as GemmParams::entries
 };
 inline size_t pulay_error_work_doubles(int n, int o) { return (size_t)padded_ld(n) * 4 * (o > 0 ? o : 1); }
 int pulay_error_fused(const PulayErrorArgs& a, cudaStream_t st);
