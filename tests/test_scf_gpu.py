@@ -722,3 +722,23 @@ def test_rescue_dump_of_failed_eigenproblem(G, tmp_path, monkeypatch):
         d = np.load(dumps[0])
         assert d["diagonalised_matrix"].shape[-2:] == (14, 14) and np.isnan(d["diagonalised_matrix"]).any()
         assert d["overlap"].shape == (14, 14)
+
+
+def test_fresh_process_sequence_that_faulted_the_tensor_map_kernel():
+    """Regression scenario of the one device fault of round 2: in a FRESH process, engines of order 14 ... 128 are created and
+    destroyed, then the 24-member ensemble of order 32 runs.  With a loose batch extent in the GEMM tensor maps the TMA unit
+    touched memory behind the last problem, which is only fatal when that memory is unmapped - i.e. after larger
+    allocations were freed (`profiles/r02_cuda_gdb_tensor_map_fault.txt`).  The child repeats exactly that order."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("GSCF_B200_IN_SEQUENCE_CHILD"):
+        pytest.skip("child of this very test")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = ("functionality or example or hooks or diis_coeff or max_iter or synthetic_parity_small or unrestricted "
+           "or ensemble_lockstep")
+    env2 = dict(os.environ, GSCF_B200_IN_SEQUENCE_CHILD="1", GSCF_B200_TMAP_STRICT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_scf_gpu.py", "-m", "gpu", "-x", "-q", "-k", sel],
+                       cwd=root, env=env2, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
