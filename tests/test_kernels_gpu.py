@@ -133,7 +133,7 @@ def test_dgemm_randomised_sweep_tensor_maps_on_small_tiles():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env2 = dict(os.environ, GSCF_B200_GEMM_TMA="4")
+    env2 = dict(os.environ, GSCF_B200_GEMM_TMA="4", GSCF_B200_TMAP_STRICT="0")  # also products smaller than one box
     r = subprocess.run([sys.executable, "scripts/gemm_fuzz.py", "150", "900"], cwd=root, env=env2, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
