@@ -1152,12 +1152,121 @@ bt_small_kernel(const double* __restrict__ Ab, int lda, long long sA, const doub
     for (int r = lane; r < n; r += 32) Z[(size_t)col * ldz + r] = sV[(size_t)col * zs + r];
 }
 
-// n <= 128 and the switch GSCF_B200_BT_SMALL (default on)
-bool bt_small_route(int n) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("GSCF_B200_BT_SMALL"); on = (e && e[0] == '0') ? 0 : 1; }
-  return on && n >= 2 && n <= BTS_NMAX;
+// Lanes along the rows (n = 128, all columns of Z): a WARP owns eight whole columns of Z - lane l keeps rows l, l + 32,
+// l + 64, l + 96 of each - so the sums over the rows are warp-level (halving butterflies: eight partials -> one per lane with
+// seven exchanges, two more for the full sum) and the reflector loop has NO block barrier; a lane reads four entries of a
+// reflector instead of having 32 of them broadcast, and Z is read and written in place with coalesced accesses (no staging).
+// Row slices that lie entirely above a reflector pair are skipped (uniform).
+constexpr int BTW_T = 512;
+inline size_t btw_smem_bytes() { return ((size_t)128 * 128 + 2 * 128 + (BTW_T / 32) * 16) * sizeof(double); }
+__global__ void __launch_bounds__(BTW_T, 1)
+bt_small_warp_kernel(const double* __restrict__ Ab, int lda, long long sA, const double* __restrict__ taub,
+                     double* __restrict__ Zb, int ldz, long long sZ, const int* __restrict__ map) {
+  constexpr int n = 128, np = 128, NWARP = BTW_T / 32;
+  extern __shared__ __align__(16) double bsm[];
+  double* sV = bsm;                 // [n][np]: column j = reflector j with explicit zeros and unit entry (row j + 1)
+  double* stau = sV + n * np;       // [n]
+  double* sdot = stau + n;          // [n]: sdot[j] = v_{j-1}^T v_j
+  double* sy = sdot + n;            // [NWARP][16]: the sixteen sums of a warp's reflector pair (a: 0..7, b: 8..15)
+  const long long q = map ? map[blockIdx.x] : blockIdx.x;
+  const double* __restrict__ A = Ab + q * sA;
+  double* __restrict__ Z = Zb + q * sZ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double z[4][8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i][c] = Z[(size_t)(8 * warp + c) * ldz + lane + 32 * i];
+  for (int j = warp; j < n; j += NWARP) {
+    const double* a = A + (size_t)j * lda;
+    for (int r = lane; r < np; r += 32)
+      sV[j * np + r] = (j < n - 1 && r > j + 1) ? a[r] : ((j < n - 1 && r == j + 1) ? 1.0 : 0.0);
+  }
+  for (int j = tid; j < n; j += BTW_T) stau[j] = j < n - 1 ? (taub + q * n)[j] : 0.0;
+  __syncthreads();
+  for (int j = 1 + warp; j < n - 1; j += NWARP) {
+    double sdt = 0.0;
+    for (int r = lane; r < np; r += 32) sdt = fma(sV[(j - 1) * np + r], sV[j * np + r], sdt);
+    sdt = warp_sum(sdt);
+    if (lane == 0) sdot[j] = sdt;
+  }
+  __syncthreads();
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  double* my = sy + warp * 16;
+  // sums over the warp of eight per-lane values; lane (h16, h8, h4) returns the total of value 4 h16 + 2 h8 + h4
+  auto reduce8 = [&](const double (&v)[8]) {
+    double a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double send = h16 ? v[i] : v[i + 4], keep = h16 ? v[i + 4] : v[i];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double send = h8 ? a4[i] : a4[i + 2], keep = h8 ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    double a1 = (h4 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h4 ? a2[0] : a2[1], 4);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    return a1;
+  };
+  const int slot = ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);  // 2 h8 + h4: column of the half this lane ends up with
+  for (int j = n - 2; j >= 0; j -= 2) {
+    // pair (a = j, b = j - 1), H_a first; the last reflector (j = 0) stands alone: b = none
+    const bool pair = j >= 1;
+    const double ta = stau[j], tb = pair ? stau[j - 1] : 0.0;
+    const int i0 = (pair ? j : j + 1) >> 5;  // first row slice with a non-zero entry of either reflector
+    double va[4], vb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      va[i] = i >= i0 ? sV[j * np + lane + 32 * i] : 0.0;
+      vb[i] = (pair && i >= i0) ? sV[(j - 1) * np + lane + 32 * i] : 0.0;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double v[8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        double pa = 0.0, pb = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i >= i0) {
+            pa = fma(va[i], z[i][4 * half + c], pa);
+            pb = fma(vb[i], z[i][4 * half + c], pb);
+          }
+        v[c] = pa;
+        v[4 + c] = pb;
+      }
+      const double tot = reduce8(v);
+      if ((lane & 3) == 0) my[(h16 ? 8 : 0) + 4 * half + slot] = tot;
+    }
+    __syncwarp();
+    const double sab = pair ? sdot[j] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double ya = ta * my[c];
+      const double yb = tb * (my[8 + c] - sab * ya);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i >= i0) z[i][c] = fma(-vb[i], yb, fma(-va[i], ya, z[i][c]));
+    }
+    __syncwarp();  // every lane has read the sums before the next pair overwrites them
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Z[(size_t)(8 * warp + c) * ldz + lane + 32 * i] = z[i][c];
 }
+
+// n <= 128 and the switch GSCF_B200_BT_SMALL (default on)
+// GSCF_B200_BT_SMALL: 0 = blocked route, 1 (default) = bt_small_kernel, 2 = bt_small_warp_kernel where it applies
+int bt_small_mode() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("GSCF_B200_BT_SMALL"); on = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+  return on;
+}
+bool bt_small_route(int n) { return bt_small_mode() != 0 && n >= 2 && n <= BTS_NMAX; }
 
 int back_transform_small(int n, const double* A, int lda, long long sA, const TrdWs& ws, double* Z, int ldz, long long sZ,
                          int batch, const int* map, cudaStream_t st, int nvec) {
@@ -1168,7 +1277,15 @@ int back_transform_small(int n, const double* A, int lda, long long sA, const Tr
   if (once.need(dev)) {
     GSCF_CUDA_TRY(cudaFuncSetAttribute(bt_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)bts_smem_bytes(BTS_NMAX)));
+    GSCF_CUDA_TRY(cudaFuncSetAttribute(bt_small_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)btw_smem_bytes()));
     once.done(dev);
+  }
+  if (bt_small_mode() == 2 && n == 128 && nz == n) {
+    bt_small_warp_kernel<<<batch, BTW_T, btw_smem_bytes(), st>>>(A, lda, sA, ws.tau, Z, ldz, sZ, map);
+    count_launch();
+    GSCF_CHECK_LAUNCH();
+    return GSCF_B200_OK;
   }
   bt_small_kernel<<<batch, BTS_T, smem, st>>>(A, lda, sA, ws.tau, n, Z, ldz, sZ, nz, map);
   count_launch();
