@@ -462,6 +462,9 @@ def test_syev_special_matrices(env, n):
     (700, 3, {"GSCF_B200_BT_PAIR": "0"}),
     (385, 2, {}),                                                                   # three blocks: one merged pair + a single block
     (300, 20, {"GSCF_B200_BT_PAIR": "2"}),                                          # merged pairs forced for a batch (64-wide blocks)
+    (128, 40, {"GSCF_B200_BT_SMALL": "2"}),                                         # fused back-transformation, lanes along the rows
+    (128, 12, {"GSCF_B200_BT_SMALL": "0"}),                                         # blocked back-transformation for small matrices
+    (100, 7, {"GSCF_B200_BT_SMALL": "0"}),
     (1024, 1, {"GSCF_B200_TF_SOLO_TAIL": "0"}),                                     # all-SM register kernel to the last column
     (1024, 2, {}),                                                                  # two matrices: tail of each in one CTA
     (2048, 1, {}),                                                                  # L2 kernel, hand-over to shared memory, then to one CTA
