@@ -8,12 +8,15 @@
 //     !TA: sA[k][m]  ld = BM+4      TA: sA[m][k]  ld = BK+4
 //     !TB: sB[n][k]  ld = BK+4      TB: sB[k][n]  ld = BN+4
 //
-// k-contiguous operands (TA / !TB: X^T Z, V^T Z, the right-hand operands of every NN product) of launches whose
-// shapes qualify are staged by TENSOR-MAP TMA instead (cp.async.bulk.tensor, SASS UTMALDG; kernel
-// dgemm_dmma_tm_kernel): a 3-D map {k, rows, batch entry} with boxes of 4 x BM (x 1) doubles lands one k-group of
-// the tile densely as s[kgroup][row][4], so the 32 lanes of a DMMA fragment (row = lane / 4, k = lane % 4) read 256
-// consecutive bytes - conflict-free without padding, which a tensor-map box cannot produce.  The m- / n-contiguous
-// operand of the same launch keeps its 1-D bulk copies; all copies of a stage complete on the stage's one mbarrier.
+// Launches whose shapes, alignment and batch extent are known on the host are staged by TENSOR-MAP TMA instead
+// (cp.async.bulk.tensor, SASS UTMALDG; kernel dgemm_dmma_tm_kernel), into DENSE tiles laid out in fragment order:
+//   k-contiguous operand (TA / !TB):      3-D map {k, rows, batch entry}, four boxes of 4 x BM per stage -> s[k / 4][row][4]
+//   m- / n-contiguous operand (!TA / TB): 4-D map {4 rows, k, row groups, batch entry} (row-group stride 32 bytes, smaller
+//                                         than the k stride), ONE box of 4 x BK x BM/4 per stage       -> s[row / 4][k][4]
+// In both layouts the lanes of a DMMA fragment (row = lane / 4, k = lane % 4) read 16 consecutive doubles per half-warp:
+// conflict-free without the padding a tensor-map box cannot produce; rows / k beyond the matrix are zero-filled by the
+// TMA unit, so there is no edge-tile path.  All copies of a stage complete on the stage's one mbarrier.  The map's batch
+// extent is the exact number of problems (see try_launch_tm for the fault a loose bound caused).
 #include "gemm.cuh"
 
 #include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled types (the entry point is fetched at run time)
