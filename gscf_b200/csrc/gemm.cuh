@@ -1,4 +1,5 @@
-// FP64 tensor-core GEMM for sm_100a (DMMA.8x8x4 tiles fed through a cp.async pipeline).
+// FP64 tensor-core GEMM for sm_100a (DMMA.8x8x4 tiles fed by tensor-map TMA; 1-D bulk copies / cp.async where a launch
+// does not qualify).
 //
 // Replaces every dense contraction the reference delegates to lazyten/BLAS: the
 // orthogonalisation X^T F X and back-transformation X C' of the generalised eigensolve
@@ -46,7 +47,8 @@ struct GemmParams {
   int ldc2;
   long long sC2;
   double alpha2;
-  int use_tma;            // stage interior tiles with TMA bulk copies (set by launch_gemm; GSCF_B200_GEMM_TMA=0 disables)
+  int use_tma;            // operand staging level, set by launch_gemm from GSCF_B200_GEMM_TMA (0 cp.async ... 3 default:
+                          // tensor maps for both operand layouts; see gemm.cu)
   int ksplit;             // > 1: split-k, blockIdx.z = entry * ksplit + split, partial tiles go to Cpart
   double* Cpart;          // [batch * ksplit][m * n] partial products (compact, ld = m)
 };
